@@ -1,0 +1,148 @@
+"""Generate tests/golden/* by executing the REAL reference modules (build container only).
+
+    python -m oracle.gen_golden
+
+TEST INFRASTRUCTURE ONLY.  The reference holds no golden vectors of its own, so
+these fixtures are "outputs of the reference itself run here": the reference's DLASeg / AFE_module /
+generic_decode (imported from /root/reference/src/lib through oracle/ref_loader.py, DCN =
+torchvision.ops.deform_conv2d shim) and torch.nn.LSTM/Linear assembled as
+utils/tracking_utils/kalman_filter_lstm.py:9-29 does (that file itself is un-importable: it
+imports the broken model.model).  Weights/inputs are the seeded synthetic tensors of oracle/spec.py, so
+the GPU box regenerates identical bits without the reference.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_loader, spec
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sample_positions(numel, n=512, tag="pos"):
+    g = torch.Generator()
+    g.manual_seed(12345 + len(tag) + numel)
+    return torch.randint(0, numel, (n,), generator=g)
+
+
+def fm_digest(t):
+    flat = t.contiguous().view(-1)
+    pos = sample_positions(flat.numel())
+    return {"shape": list(t.shape), "sum": float(flat.double().sum()), "abssum": float(flat.double().abs().sum()),
+            "max": float(flat.abs().max()), "pos": pos, "val": flat[pos].clone()}
+
+
+def gen_frame(name, heads, dataset, H, W, N, n_prev, max_object, K):
+    m, opt = ref_loader.build_dlaseg(heads, dataset=dataset, max_object=max_object)
+    sp = spec.dlaseg_spec(heads, dataset=dataset)
+    sd = spec.make_state_dict(sp)
+    m.load_state_dict(sd, strict=True)
+    x = spec.make_input((1, 3, H, W), tag="image")
+    centres = spec.make_uniform((1, N, 1, 1, 2), -1.05, 1.05, tag="centres")      # some beyond the border
+    centres_prev = spec.make_uniform((1, n_prev, 1, 1, 2), -1.0, 1.0, tag="centres_prev")
+    _, _, decode = ref_loader.load()
+    with torch.no_grad():
+        out, fm = m(x)
+        emb = m.AFE.forward_feature_extracter(fm, centres)
+        emb_prev = m.AFE.forward_feature_extracter(fm, centres_prev)
+        aff = m.AFE.forward_stacker_features(emb_prev, emb, False)
+        aff_fill = m.AFE.forward_stacker_features(emb_prev, emb, True)
+        aff_full = m.AFE.forward_stacker_features(emb, emb, False)
+        sig = {k: v.clone() for k, v in out[0].items()}
+        sig["hm"] = sig["hm"].sigmoid_()
+        if "dep" in sig:
+            sig["dep"] = 1.0 / (sig["dep"].sigmoid() + 1e-6) - 1.0
+        dec = decode.generic_decode({k: v.clone() for k, v in sig.items()}, K=K, opt=opt)
+    g = {"meta": dict(heads=dict(heads), dataset=dataset, H=H, W=W, N=N, n_prev=n_prev, max_object=max_object, K=K, seed=317),
+         "heads": {k: v.clone() for k, v in out[0].items()},
+         "fm": [fm_digest(f) for f in fm],
+         "emb": emb.clone(), "emb_prev": emb_prev.clone(),
+         "aff": torch.from_numpy(aff.copy()), "aff_fill": torch.from_numpy(aff_fill.copy()),
+         "aff_full": torch.from_numpy(aff_full.copy()),
+         "decode": {k: v.clone() for k, v in dec.items()}}
+    torch.save(g, os.path.join(OUT, name + ".pt"))
+    keys = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, f"state_dict_keys_{dataset}_{len(heads)}heads.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+    print(name, "ok;", len(keys), "keys")
+
+
+def gen_dcn():
+    """One reference DeformConv module (dla.py:646-665) per (chi, cho, h, w) at small sizes."""
+    dla, _, _ = ref_loader.load()
+    cases = []
+    for (chi, cho, h, w) in ((64, 64, 24, 40), (128, 64, 12, 20), (512, 256, 5, 9), (256, 128, 9, 7)):
+        mod = dla.DeformConv(chi, cho).eval()
+        sp = {}
+        spec._deform(sp, "d", chi, cho)
+        sd = spec.make_state_dict(sp, seed=1000 + chi + cho)
+        mod.load_state_dict({k[2:]: v for k, v in sd.items()}, strict=True)
+        x = spec.make_input((1, chi, h, w), tag=f"dcn{chi}x{cho}")
+        with torch.no_grad():
+            y = mod(x)
+        cases.append({"chi": chi, "cho": cho, "h": h, "w": w, "seed": 1000 + chi + cho, "y": y.clone()})
+    torch.save(cases, os.path.join(OUT, "dcn_layers.pt"))
+    print("dcn ok")
+
+
+def gen_decode_plateau():
+    """Adversarial decode: plateaus/ties.  Records what the reference's generic_decode (torch.topk on
+    this build) returns so the tie rule is documented by data."""
+    _, _, decode = ref_loader.load()
+    opt = ref_loader.make_opt()
+    g = torch.Generator(); g.manual_seed(99)
+    B, C, H, W, K = 2, 3, 16, 24, 12
+    # heat quantised to 1/8 steps => many exact ties between distinct isolated peaks
+    hm = (torch.rand(B, C, H, W, generator=g) * 8).floor() / 8 * 0.9 + 0.05
+    out = {"hm": hm.clone(), "reg": torch.rand(B, 2, H, W, generator=g), "wh": torch.randn(B, 2, H, W, generator=g),
+           "tracking": torch.randn(B, 2, H, W, generator=g), "ltrb_amodal": torch.randn(B, 4, H, W, generator=g)}
+    with torch.no_grad():
+        dec = decode.generic_decode({k: v.clone() for k, v in out.items()}, K=K, opt=opt)
+    torch.save({"in": out, "K": K, "decode": dec}, os.path.join(OUT, "decode_plateau.pt"))
+    print("decode plateau ok")
+
+
+def gen_lstm():
+    res = {}
+    for dataset, fin, fout, fut in (("mot", 11, 20, 5), ("nuscenes", 18, 16, 4)):
+        lstm = torch.nn.LSTM(fin, 128)                      # kalman_filter_lstm.py:13-20
+        out1 = torch.nn.Linear(128, 64)
+        out2 = torch.nn.Linear(64, fout)
+        sd = spec.make_state_dict(spec.lstm_spec(dataset), seed=55)
+        lstm.load_state_dict({k[5:]: v for k, v in sd.items() if k.startswith("lstm.")})
+        out1.load_state_dict({"weight": sd["out1.weight"], "bias": sd["out1.bias"]})
+        out2.load_state_dict({"weight": sd["out2.weight"], "bias": sd["out2.bias"]})
+        T = 7
+        h0 = spec.make_input((T, 128), tag="h0") * 0.1
+        c0 = spec.make_input((T, 128), tag="c0") * 0.1
+        x = spec.make_input((T, fin), tag="lstm_x")
+        hn, cn, pred = [], [], []
+        with torch.no_grad():
+            for t in range(T):                              # one track at a time, like tracker.py:467
+                nf = x[t].view(1, 1, fin).permute(1, 0, 2)  # predict(): permute(1,0,2)
+                o, (h, c) = lstm(nf, (h0[t].view(1, 1, 128), c0[t].view(1, 1, 128)))
+                y = out2(out1(o[-1]))
+                hn.append(h.view(128)); cn.append(c.view(128)); pred.append(y.view(fut, -1))
+        res[dataset] = {"T": T, "hn": torch.stack(hn), "cn": torch.stack(cn), "pred": torch.stack(pred)}
+    torch.save(res, os.path.join(OUT, "lstm_step.pt"))
+    print("lstm ok")
+
+
+def main():
+    if not ref_loader.available():
+        sys.exit("reference not present; goldens can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_frame("frame_mot_96x128", spec.MOT_HEADS, "mot", 96, 128, N=10, n_prev=7, max_object=100, K=20)
+    gen_frame("frame_kitti_64x160", spec.KITTI_HEADS, "kitti", 64, 160, N=6, n_prev=6, max_object=100, K=15)
+    gen_frame("frame_nusc_64x96", spec.NUSC_HEADS, "nuscenes", 64, 96, N=9, n_prev=4, max_object=30, K=25)
+    gen_dcn()
+    gen_decode_plateau()
+    gen_lstm()
+
+
+if __name__ == "__main__":
+    main()

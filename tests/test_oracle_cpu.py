@@ -1,0 +1,138 @@
+"""CPU suite, part 1: the oracle restatement is pinned to tests/golden (outputs of the REAL reference
+modules, oracle/gen_golden.py) and, when /root/reference is present, re-checked live against it."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, nerr
+from oracle import ref_loader, restate, spec
+
+TOL = 2e-5   # two fp32 CPU evaluations of the same formulas (different op order)
+
+FRAMES = [("frame_mot_96x128", spec.MOT_HEADS, "mot"), ("frame_kitti_64x160", spec.KITTI_HEADS, "kitti"),
+          ("frame_nusc_64x96", spec.NUSC_HEADS, "nuscenes")]
+
+
+@pytest.mark.parametrize("name,heads,dataset", FRAMES)
+def test_state_dict_inventory(name, heads, dataset):
+    with open(os.path.join(GOLDEN, f"state_dict_keys_{dataset}_{len(heads)}heads.json")) as f:
+        ref = {k: tuple(v) for k, v in json.load(f).items()}
+    mine = {k: tuple(s) for k, (_, s) in spec.dlaseg_spec(heads, dataset=dataset).items()}
+    assert mine == ref
+
+
+@pytest.mark.parametrize("name,heads,dataset", FRAMES)
+@pytest.mark.parametrize("explicit", [False, True])
+def test_frame_restatement_vs_reference_golden(name, heads, dataset, explicit):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    mt = g["meta"]
+    sd = spec.make_state_dict(spec.dlaseg_spec(heads, dataset=dataset))
+    x = spec.make_input((1, 3, mt["H"], mt["W"]), tag="image")
+    with torch.no_grad():
+        out, fm = restate.dlaseg_forward(sd, x, heads, explicit=explicit)
+    for h in heads:
+        assert nerr(out[0][h], g["heads"][h]) < TOL, h
+    assert len(fm) == 13
+    for i, (f, d) in enumerate(zip(fm, g["fm"])):
+        assert list(f.shape) == d["shape"]
+        assert nerr(f.contiguous().view(-1)[d["pos"]], d["val"]) < TOL * 5, i
+        assert abs(float(f.double().abs().sum()) - d["abssum"]) / d["abssum"] < 1e-5
+    centres = spec.make_uniform((1, mt["N"], 1, 1, 2), -1.05, 1.05, tag="centres")
+    centres_prev = spec.make_uniform((1, mt["n_prev"], 1, 1, 2), -1.0, 1.0, tag="centres_prev")
+    with torch.no_grad():
+        emb = restate.afe_extract(sd, fm, centres)
+        emb_prev = restate.afe_extract(sd, fm, centres_prev)
+    assert nerr(emb, g["emb"]) < TOL * 5
+    assert nerr(emb_prev, g["emb_prev"]) < TOL * 5
+    P = mt["max_object"]
+    with torch.no_grad():
+        assert nerr(restate.afe_affinity(sd, g["emb_prev"], g["emb"], P, False), g["aff"]) < 1e-5
+        assert nerr(restate.afe_affinity(sd, g["emb_prev"], g["emb"], P, True), g["aff_fill"]) < 1e-5
+        assert nerr(restate.afe_affinity(sd, g["emb"], g["emb"], P, False), g["aff_full"]) < 1e-5
+    # decode on the reference's own (sigmoided) heads: bit-exact
+    sig = restate.sigmoid_output(g["heads"])
+    dec = restate.generic_decode(sig, K=mt["K"])
+    for k, v in g["decode"].items():
+        assert torch.equal(dec[k], v), k
+
+
+def test_decode_plateau_ties_bit_exact():
+    g = torch.load(os.path.join(GOLDEN, "decode_plateau.pt"), weights_only=False)
+    dec = restate.generic_decode(g["in"], K=g["K"])
+    # scores and boxes must be bit-exact; among exactly tied scores torch.topk's order is
+    # implementation-defined, so indices are compared as per-score multisets
+    assert torch.equal(dec["scores"], g["decode"]["scores"])
+    for b in range(dec["scores"].shape[0]):
+        mine = sorted(zip(dec["scores"][b].tolist(), dec["clses"][b].tolist(), dec["ys"][b].tolist(), dec["xs"][b].tolist()))
+        ref = sorted(zip(g["decode"]["scores"][b].tolist(), g["decode"]["clses"][b].tolist(),
+                         g["decode"]["ys"][b].tolist(), g["decode"]["xs"][b].tolist()))
+        # strictly-greater-than-threshold part must agree exactly
+        thr = dec["scores"][b].min().item()
+        assert [m for m in mine if m[0] > thr] == [r for r in ref if r[0] > thr]
+
+
+def test_dcn_layers_vs_reference_golden():
+    cases = torch.load(os.path.join(GOLDEN, "dcn_layers.pt"), weights_only=False)
+    for c in cases:
+        sp = {}
+        spec._deform(sp, "d", c["chi"], c["cho"])
+        sd = spec.make_state_dict(sp, seed=c["seed"])
+        x = spec.make_input((1, c["chi"], c["h"], c["w"]), tag=f"dcn{c['chi']}x{c['cho']}")
+        with torch.no_grad():
+            for explicit in (False, True):
+                y = restate.deform_conv(sd, "d", x, explicit=explicit)
+                assert nerr(y, c["y"]) < TOL, (c["chi"], c["cho"], explicit)
+
+
+def test_dcn_identities():
+    """Known-answer identities of SURVEY.md section 4: zero offset/mask conv => 0.5*conv2d+b; integer
+    offsets + mask=1 => shifted conv."""
+    g = torch.Generator(); g.manual_seed(3)
+    x = torch.randn(1, 8, 9, 11, generator=g)
+    w = torch.randn(6, 8, 3, 3, generator=g) * 0.2
+    b = torch.randn(6, generator=g)
+    off = torch.zeros(1, 18, 9, 11)
+    m = torch.full((1, 9, 9, 11), 0.5)
+    y = restate.dcn_v2_explicit(x, off, m, w, b)
+    ref = 0.5 * torch.nn.functional.conv2d(x, w, None, padding=1) + b.view(1, -1, 1, 1)
+    assert nerr(y, ref) < 1e-6
+    off[:, 0::2] = 1.0      # dy = +1 on every tap -> one-row shift
+    y = restate.dcn_v2_explicit(x, off, torch.ones(1, 9, 9, 11), w, b)
+    # rows shifted by one: sample(h-1+ky+1) ; zero beyond the border (row H is outside)
+    xpad = torch.nn.functional.pad(x, (1, 1, 1, 2))     # rows -1..H+1
+    ref = torch.nn.functional.conv2d(xpad[:, :, 1:], w, None) + b.view(1, -1, 1, 1)
+    assert nerr(y, ref) < 1e-6
+
+
+def test_lstm_restatement_vs_torch_lstm_golden():
+    g = torch.load(os.path.join(GOLDEN, "lstm_step.pt"), weights_only=False)
+    for dataset, fin, fut in (("mot", 11, 5), ("nuscenes", 18, 4)):
+        sd = spec.make_state_dict(spec.lstm_spec(dataset), seed=55)
+        T = g[dataset]["T"]
+        h0 = spec.make_input((T, 128), tag="h0") * 0.1
+        c0 = spec.make_input((T, 128), tag="c0") * 0.1
+        x = spec.make_input((T, fin), tag="lstm_x")
+        hn, cn, pred = restate.lstm_predict(sd, h0, c0, x, fut)
+        assert nerr(hn, g[dataset]["hn"]) < 1e-6
+        assert nerr(cn, g[dataset]["cn"]) < 1e-6
+        assert nerr(pred, g[dataset]["pred"]) < 1e-5
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_live_reference_affinity_depends_on_max_object():
+    """The dual softmax denominators include (max_object - n) zero entries (AFE.py:123-134)."""
+    sd = spec.make_state_dict(spec.dlaseg_spec(spec.MOT_HEADS))
+    xp = spec.make_input((1, 5, 416), tag="xp").abs()
+    xn = spec.make_input((1, 6, 416), tag="xn").abs()
+    with torch.no_grad():
+        a = restate.afe_affinity(sd, xp, xn, 100, False)
+        b = restate.afe_affinity(sd, xp, xn, 200, False)
+        _, AFE, _ = ref_loader.load()
+        mod = AFE.AFE_module(ref_loader.make_opt(max_object=200)).eval()
+        mod.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("AFE.")})
+        ref = mod.forward_stacker_features(xp, xn, False)
+    assert np.abs(a - b).max() > 1e-3
+    assert nerr(b, ref) < 1e-5
