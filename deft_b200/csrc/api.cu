@@ -1,0 +1,31 @@
+// Library-level entry points: version, error string, device check.
+#include "common.cuh"
+#include <string.h>
+
+namespace deft {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace deft
+
+extern "C" {
+int deft_version(void) { return 100; }
+const char* deft_last_error(void) { return deft::g_err; }
+int deft_device_ok(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        deft::set_error("no CUDA device");
+        return 0;
+    }
+    if (p.major != 10) {
+        deft::set_error("deft_b200 is built for sm_100a only; found sm_%d%d", p.major, p.minor);
+        return 0;
+    }
+    return 1;
+}
+}

@@ -1,0 +1,547 @@
+// Non-conv entry points: sigmoid_output, CenterNet decode (NMS + exact two-stage top-K + gathers),
+// AFE sparse embedding extractor, AFE pairwise-MLP affinity + dual softmax, batched LSTM step.
+#include "igemm_simt.cuh"
+#include "tc_engine.cuh"
+
+namespace deft {
+
+// ================================================================================================
+// a6: sigmoid_output
+__global__ void sigmoid_output_kernel(float* hm, size_t n_hm, float* dep, size_t n_dep, float depth_scale) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t j = i; j < n_hm; j += stride) hm[j] = sigmoidf_(hm[j]);
+    for (size_t j = i; j < n_dep; j += stride) dep[j] = (1.0f / (sigmoidf_(dep[j]) + 1e-6f) - 1.0f) * depth_scale;
+}
+
+// ================================================================================================
+// a6: decode
+__device__ __forceinline__ uint32_t f2u(float f) {
+    f = f + 0.0f;  // -0 -> +0
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// vals = heat * (maxpool3x3(heat) == heat)   (utils.py:69-74)
+__global__ void nms_kernel(const float* __restrict__ hm, float* __restrict__ vals, int H, int W, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int p = (int)(i % ((size_t)H * W));
+        int y = p / W, x = p - y * W;
+        const float* pl = hm + (i - p);
+        float h = pl[p], m = h;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                int yy = y + dy, xx = x + dx;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m = fmaxf(m, pl[yy * W + xx]);
+            }
+        vals[i] = (m == h) ? h : 0.0f;
+    }
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* a, int n /* pow2 */) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                int ixj = t ^ j;
+                if (ixj > t) {
+                    unsigned long long x = a[t], y = a[ixj];
+                    bool desc = (t & k) == 0;
+                    if (desc ? (x < y) : (x > y)) { a[t] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Per (class, batch) plane: exact top-K by (value desc, index asc).  Radix select for the K-th value,
+// ordered compaction of the winners, bitonic sort.  blockDim = 1024.
+__global__ void __launch_bounds__(1024) topk_class_kernel(const float* __restrict__ vals, int HW, int K,
+                                                          unsigned long long* __restrict__ cand) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_kk;
+    __shared__ unsigned int wcnt_gt[32], wcnt_eq[32];
+    __shared__ unsigned int run_gt, run_eq;
+    __shared__ unsigned long long keys[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* v = vals + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * HW;
+    unsigned long long* out = cand + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * K;
+
+    unsigned int prefix = 0, mask = 0, kk = K;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < HW; i += 1024) {
+            unsigned int u = f2u(v[i]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int cum = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (cum + hist[b] >= kk) break;
+                cum += hist[b];
+            }
+            s_prefix = prefix | ((unsigned int)b << shift);
+            s_kk = kk - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        kk = s_kk;
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    const unsigned int T = prefix;          // K-th largest value (as ordered uint)
+    const unsigned int n_gt = K - kk;       // strictly greater elements; kk ties to take in index order
+    if (tid == 0) { run_gt = 0; run_eq = 0; }
+    int Kp = 1;
+    while (Kp < K) Kp <<= 1;
+    for (int i = tid; i < Kp; i += 1024) keys[i] = 0ull;
+    __syncthreads();
+    for (int base = 0; base < HW; base += 1024) {
+        int i = base + tid;
+        unsigned int u = (i < HW) ? f2u(v[i]) : 0u;
+        bool gt = (i < HW) && (u > T);
+        bool eq = (i < HW) && (u == T);
+        unsigned int bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) { wcnt_gt[warp] = __popc(bg); wcnt_eq[warp] = __popc(be); }
+        __syncthreads();
+        unsigned int og = run_gt, oe = run_eq;
+        for (int w = 0; w < warp; ++w) { og += wcnt_gt[w]; oe += wcnt_eq[w]; }
+        unsigned int lm = (1u << lane) - 1u;
+        og += __popc(bg & lm);
+        oe += __popc(be & lm);
+        unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
+        if (gt) keys[og] = key;
+        if (eq && oe < kk) keys[n_gt + oe] = key;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int tg = 0, te = 0;
+            for (int w = 0; w < 32; ++w) { tg += wcnt_gt[w]; te += wcnt_eq[w]; }
+            run_gt += tg;
+            run_eq += te;
+        }
+        __syncthreads();
+    }
+    bitonic_sort_desc(keys, Kp);
+    for (int i = tid; i < K; i += 1024) out[i] = keys[i];
+}
+
+struct DecodeArgs {
+    const float* vals;
+    const unsigned long long* cand;
+    const float* reg;
+    const float* wh;
+    const float* ltrb;
+    float* scores; long long* inds; int* clses; float* ys; float* xs; float* bboxes; float* bboxes_amodal;
+    int C, H, W, K;
+};
+
+// Second stage (utils.py:98-104) + gathers + box arithmetic (decode.py:113-183).  One block per image.
+__global__ void __launch_bounds__(1024) decode_merge_kernel(DecodeArgs a, int Np) {
+    extern __shared__ unsigned long long skeys[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int CK = a.C * a.K, HW = a.H * a.W;
+    const unsigned long long* cand = a.cand + (size_t)b * CK;
+    for (int i = tid; i < Np; i += blockDim.x) {
+        unsigned long long k = 0ull;
+        if (i < CK) k = (cand[i] & 0xFFFFFFFF00000000ull) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
+        skeys[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_desc(skeys, Np);
+    for (int k = tid; k < a.K; k += blockDim.x) {
+        unsigned int flatpos = 0xFFFFFFFFu - (unsigned int)(skeys[k] & 0xFFFFFFFFull);
+        int cls = (int)(flatpos / (unsigned int)a.K);
+        unsigned int idx = 0xFFFFFFFFu - (unsigned int)(cand[flatpos] & 0xFFFFFFFFull);
+        float score = a.vals[((size_t)b * a.C + cls) * HW + idx];
+        int yi = (int)(idx / (unsigned int)a.W), xi = (int)(idx - (unsigned int)yi * a.W);
+        float ys0 = (float)yi, xs0 = (float)xi;
+        size_t o = (size_t)b * a.K + k;
+        a.scores[o] = score; a.inds[o] = (long long)idx; a.clses[o] = cls; a.ys[o] = ys0; a.xs[o] = xs0;
+        float xs = __fadd_rn(xs0, 0.5f), ys = __fadd_rn(ys0, 0.5f);
+        if (a.reg) {
+            xs = __fadd_rn(xs0, a.reg[((size_t)b * 2 + 0) * HW + idx]);
+            ys = __fadd_rn(ys0, a.reg[((size_t)b * 2 + 1) * HW + idx]);
+        }
+        if (a.wh && a.bboxes) {
+            float w0 = a.wh[((size_t)b * 2 + 0) * HW + idx], w1 = a.wh[((size_t)b * 2 + 1) * HW + idx];
+            if (w0 < 0.f) w0 = 0.f;
+            if (w1 < 0.f) w1 = 0.f;
+            float hw0 = __fmul_rn(w0, 0.5f), hw1 = __fmul_rn(w1, 0.5f);
+            a.bboxes[o * 4 + 0] = __fsub_rn(xs, hw0); a.bboxes[o * 4 + 1] = __fsub_rn(ys, hw1);
+            a.bboxes[o * 4 + 2] = __fadd_rn(xs, hw0); a.bboxes[o * 4 + 3] = __fadd_rn(ys, hw1);
+        }
+        if (a.ltrb) {
+            float l0 = a.ltrb[((size_t)b * 4 + 0) * HW + idx], l1 = a.ltrb[((size_t)b * 4 + 1) * HW + idx];
+            float l2 = a.ltrb[((size_t)b * 4 + 2) * HW + idx], l3 = a.ltrb[((size_t)b * 4 + 3) * HW + idx];
+            float bb0 = __fadd_rn(xs0, l0), bb1 = __fadd_rn(ys0, l1), bb2 = __fadd_rn(xs0, l2), bb3 = __fadd_rn(ys0, l3);
+            if (a.bboxes_amodal) { a.bboxes_amodal[o * 4 + 0] = bb0; a.bboxes_amodal[o * 4 + 1] = bb1; a.bboxes_amodal[o * 4 + 2] = bb2; a.bboxes_amodal[o * 4 + 3] = bb3; }
+            if (a.bboxes) { a.bboxes[o * 4 + 0] = bb0; a.bboxes[o * 4 + 1] = bb1; a.bboxes[o * 4 + 2] = bb2; a.bboxes[o * 4 + 3] = bb3; }
+        }
+    }
+}
+
+__global__ void gather_feat_kernel(const float* __restrict__ feat, int C, int HW, const long long* __restrict__ inds, int K,
+                                   float* __restrict__ out, int total) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = i % C;
+    int k = (i / C) % K;
+    int b = i / (C * K);
+    out[i] = feat[((size_t)b * C + c) * HW + inds[(size_t)b * K + k]];
+}
+
+// ================================================================================================
+// a7: AFE sparse extractor.  grid (N, 13), 256 threads: thread = (corner 0..3, out channel 0..63).
+struct AfeArgs {
+    const float* map[DEFT_AFE_MAPS];
+    const float* w[DEFT_AFE_MAPS];
+    const float* b[DEFT_AFE_MAPS];
+    int pitch[DEFT_AFE_MAPS], C[DEFT_AFE_MAPS], H[DEFT_AFE_MAPS], W[DEFT_AFE_MAPS], Co[DEFT_AFE_MAPS], off[DEFT_AFE_MAPS];
+    int Cemb, align_corners;
+};
+__global__ void __launch_bounds__(256) afe_extract_kernel(AfeArgs a, const float* __restrict__ centres, float* __restrict__ emb) {
+    __shared__ __align__(16) float patch[16 * 512];
+    __shared__ float res[4][64];
+    __shared__ float cw[4];
+    const int n = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
+    const int C = a.C[k], H = a.H[k], W = a.W[k], Co = a.Co[k], pitch = a.pitch[k];
+    float gx = centres[n * 2 + 0], gy = centres[n * 2 + 1];
+    float ix, iy;
+    if (a.align_corners) { ix = ((gx + 1.f) / 2.f) * (float)(W - 1); iy = ((gy + 1.f) / 2.f) * (float)(H - 1); }
+    else { ix = ((gx + 1.f) * (float)W - 1.f) / 2.f; iy = ((gy + 1.f) * (float)H - 1.f) / 2.f; }
+    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));   // padding_mode = border
+    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy;
+    if (tid == 0) {
+        float tx = ix - fx, ty = iy - fy;   // (ix - x0), (iy - y0); x1 - ix = 1 - tx
+        cw[0] = (fx + 1.f - ix) * (fy + 1.f - iy);  // nw
+        cw[1] = tx * (fy + 1.f - iy);               // ne
+        cw[2] = (fx + 1.f - ix) * ty;               // sw
+        cw[3] = tx * ty;                            // se
+    }
+    // 4x4 pixel patch around (y0-1..y0+2, x0-1..x0+2), zero outside the map (conv zero padding)
+    const float* m = a.map[k];
+    const int C4 = C / 4;
+    for (int i = tid; i < 16 * C4; i += 256) {
+        int pp = i / C4, c4 = i - pp * C4;
+        int yy = y0 - 1 + (pp >> 2), xx = x0 - 1 + (pp & 3);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ldg4(m + ((size_t)yy * W + xx) * pitch + c4 * 4);
+        *reinterpret_cast<float4*>(&patch[pp * C + c4 * 4]) = v;
+    }
+    __syncthreads();
+    const int corner = tid >> 6, o = tid & 63;
+    const int cy = corner >> 1, cx = corner & 1;
+    const bool inb = (y0 + cy <= H - 1) && (x0 + cx <= W - 1);
+    float acc = 0.f;
+    if (o < Co && inb) {
+        const float* wk = a.w[k];
+        acc = a.b[k][o];
+        for (int tap = 0; tap < 9; ++tap) {
+            int ky = tap / 3, kx = tap - ky * 3;
+            const float* pr = &patch[((cy + ky) * 4 + (cx + kx)) * C];
+            const float* wr = wk + (size_t)tap * C * Co + o;
+            for (int ci = 0; ci < C; ci += 4) {
+                float4 pv = *reinterpret_cast<const float4*>(pr + ci);
+                float w0 = __ldg(wr + (size_t)(ci + 0) * Co), w1 = __ldg(wr + (size_t)(ci + 1) * Co);
+                float w2 = __ldg(wr + (size_t)(ci + 2) * Co), w3 = __ldg(wr + (size_t)(ci + 3) * Co);
+                acc += pv.x * w0; acc += pv.y * w1; acc += pv.z * w2; acc += pv.w * w3;
+            }
+        }
+        acc = fmaxf(acc, 0.f);
+    }
+    res[corner][o] = (o < Co && inb) ? acc * cw[corner] : 0.f;
+    __syncthreads();
+    if (tid < Co) emb[(size_t)n * a.Cemb + a.off[k] + tid] = res[0][tid] + res[1][tid] + res[2][tid] + res[3][tid];
+}
+
+// ================================================================================================
+// a8: affinity tail.  S[p] = relu(h4[p,:64] . w5 + b5); then the dual softmax.
+__global__ void affinity_final_kernel(const float* __restrict__ h4, const float* __restrict__ w5, float b5, float* __restrict__ S, int M) {
+    int p = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);   // 8 lanes per pair
+    int l = threadIdx.x & 7;
+    float s = 0.f;
+    if (p < M) {
+        const float* r = h4 + (size_t)p * 64 + l * 8;
+        float4 a = ldg4(r), b = ldg4(r + 4), wa = ldg4(w5 + l * 8), wb = ldg4(w5 + l * 8 + 4);
+        s = a.x * wa.x + a.y * wa.y + a.z * wa.z + a.w * wa.w + b.x * wb.x + b.y * wb.y + b.z * wb.z + b.w * wb.w;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (p < M && l == 0) S[p] = fmaxf(s + b5, 0.f);
+}
+
+struct SoftmaxArgs {
+    int n[AFF_MAX_FRAMES];
+    int off[AFF_MAX_FRAMES + 1];
+    int m, P;
+};
+// One block per memory frame.  X = [[S (n x m), 0...; 0...], ones row/col] of size (P+1)^2 as in
+// AFE.py:123-134; rows/cols beyond n/m are exact zeros and enter the denominators analytically.
+__global__ void __launch_bounds__(256) affinity_softmax_kernel(const float* __restrict__ S, SoftmaxArgs a, float* __restrict__ out) {
+    extern __shared__ float sm[];
+    const int P = a.P, m = a.m, f = blockIdx.x, n = a.n[f];
+    float* rmax = sm; float* rsum = sm + P; float* cmax = sm + 2 * P; float* csum = sm + 3 * P;
+    const float* Sf = S + a.off[f];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < n; i += 8) {
+        float mx = 1.0f;                       // the appended false-object column
+        if (m < P) mx = fmaxf(mx, 0.f);
+        for (int j = lane; j < m; j += 32) mx = fmaxf(mx, Sf[i * m + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float s = 0.f;
+        for (int j = lane; j < m; j += 32) s += expf(Sf[i * m + j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { rmax[i] = mx; rsum[i] = s + (float)(P - m) * expf(0.f - mx) + expf(1.0f - mx); }
+    }
+    for (int j = tid; j < m; j += 256) {
+        float mx = 1.0f;
+        if (n < P) mx = fmaxf(mx, 0.f);
+        for (int i = 0; i < n; ++i) mx = fmaxf(mx, Sf[i * m + j]);
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += expf(Sf[i * m + j] - mx);
+        cmax[j] = mx;
+        csum[j] = s + (float)(P - n) * expf(0.f - mx) + expf(1.0f - mx);
+    }
+    __syncthreads();
+    float* of = out + (size_t)f * P * (P + 1);
+    for (int idx = tid; idx < n * (m + 1); idx += 256) {
+        int i = idx / (m + 1), j = idx - i * (m + 1);
+        float v;
+        if (j < m) {
+            float s = Sf[i * m + j];
+            v = fmaxf(expf(s - rmax[i]) / rsum[i], expf(s - cmax[j]) / csum[j]);
+        } else {
+            v = expf(1.0f - rmax[i]) / rsum[i];
+        }
+        of[(size_t)i * (P + 1) + j] = v;
+    }
+}
+
+// ================================================================================================
+// a10: batched single LSTM step + out1 + out2.  One block (128 threads) per track.
+__global__ void __launch_bounds__(128) lstm_step_kernel(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ c,
+                                                        const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                                        const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2, int F, int nout,
+                                                        float* __restrict__ h_out, float* __restrict__ c_out, float* __restrict__ pred) {
+    __shared__ float gates[512];
+    __shared__ __align__(16) float hn[128];
+    __shared__ __align__(16) float o1[64];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4 hv = ldg4(h + (size_t)t * 128 + lane * 4);
+    const float xv = (lane < F) ? x[(size_t)t * F + lane] : 0.f;
+    for (int r = warp * 128; r < warp * 128 + 128; ++r) {
+        float4 w = ldg4(w_hh + (size_t)r * 128 + lane * 4);
+        float s = w.x * hv.x + w.y * hv.y + w.z * hv.z + w.w * hv.w;
+        if (lane < F) s += __ldg(w_ih + (size_t)r * F + lane) * xv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) gates[r] = s + b_ih[r] + b_hh[r];
+    }
+    __syncthreads();
+    {
+        float ig = sigmoidf_(gates[tid]), fg = sigmoidf_(gates[128 + tid]);
+        float gg = tanhf(gates[256 + tid]), og = sigmoidf_(gates[384 + tid]);
+        float cn = fg * c[(size_t)t * 128 + tid] + ig * gg;
+        float hh = og * tanhf(cn);
+        c_out[(size_t)t * 128 + tid] = cn;
+        h_out[(size_t)t * 128 + tid] = hh;
+        hn[tid] = hh;
+    }
+    __syncthreads();
+    {
+        const float4 hq = *reinterpret_cast<const float4*>(&hn[lane * 4]);
+        for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+            float4 w = ldg4(w1 + (size_t)r * 128 + lane * 4);
+            float s = w.x * hq.x + w.y * hq.y + w.z * hq.z + w.w * hq.w;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) o1[r] = s + b1[r];
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < nout; r += 4) {
+        float s = __ldg(w2 + (size_t)r * 64 + lane) * o1[lane] + __ldg(w2 + (size_t)r * 64 + 32 + lane) * o1[32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) pred[(size_t)t * nout + r] = s + b2[r];
+    }
+}
+
+}  // namespace deft
+
+using namespace deft;
+
+extern "C" {
+
+int deft_sigmoid_output(float* hm, size_t n_hm, float* dep, size_t n_dep, float depth_scale, deft_stream_t s) {
+    size_t n = n_hm > n_dep ? n_hm : n_dep;
+    if (n == 0) return DEFT_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sigmoid_output_kernel<<<blocks, 256, 0, to_stream(s)>>>(hm, hm ? n_hm : 0, dep, dep ? n_dep : 0, depth_scale);
+    DEFT_CHECK_LAUNCH("sigmoid_output");
+    return DEFT_OK;
+}
+
+size_t deft_decode_workspace_bytes(int B, int C, int H, int W, int K) {
+    return align_up((size_t)B * C * H * W * sizeof(float), 256) + align_up((size_t)B * C * K * sizeof(unsigned long long), 256);
+}
+
+int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float* reg, const float* wh, const float* ltrb_amodal,
+                float* scores, int64_t* inds, int32_t* clses, float* ys, float* xs, float* bboxes, float* bboxes_amodal,
+                void* ws, size_t ws_bytes, deft_stream_t s) {
+    DEFT_REQUIRE(hm && scores && inds && clses && ys && xs && ws, "decode: null argument");
+    DEFT_REQUIRE(K >= 1 && K <= 1024 && K <= H * W, "decode: K must be in [1, min(1024, H*W)] (K=%d)", K);
+    int Np = 1;
+    while (Np < C * K) Np <<= 1;
+    DEFT_REQUIRE(Np <= 16384, "decode: C*K too large (%d)", C * K);
+    if (ws_bytes < deft_decode_workspace_bytes(B, C, H, W, K)) {
+        set_error("decode: workspace too small");
+        return DEFT_EWORKSPACE;
+    }
+    float* vals = reinterpret_cast<float*>(ws);
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + align_up((size_t)B * C * H * W * sizeof(float), 256));
+    size_t total = (size_t)B * C * H * W;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    nms_kernel<<<blocks, 256, 0, to_stream(s)>>>(hm, vals, H, W, total);
+    DEFT_CHECK_LAUNCH("nms");
+    topk_class_kernel<<<dim3(C, B), 1024, 0, to_stream(s)>>>(vals, H * W, K, cand);
+    DEFT_CHECK_LAUNCH("topk_class");
+    DecodeArgs a{vals, cand, reg, wh, ltrb_amodal, scores, (long long*)inds, clses, ys, xs, bboxes, bboxes_amodal, C, H, W, K};
+    size_t smem = (size_t)Np * sizeof(unsigned long long);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+    }
+    decode_merge_kernel<<<B, 1024, smem, to_stream(s)>>>(a, Np);
+    DEFT_CHECK_LAUNCH("decode_merge");
+    return DEFT_OK;
+}
+
+int deft_gather_feat(const float* feat, int B, int C, int HW, const int64_t* inds, int K, float* out, deft_stream_t s) {
+    DEFT_REQUIRE(feat && inds && out && B > 0 && C > 0 && K > 0, "gather_feat: bad args");
+    int total = B * K * C;
+    gather_feat_kernel<<<ceil_div(total, 256), 256, 0, to_stream(s)>>>(feat, C, HW, (const long long*)inds, K, out, total);
+    DEFT_CHECK_LAUNCH("gather_feat");
+    return DEFT_OK;
+}
+
+int deft_afe_extract(const float* const* maps, const int* pitch, const int* C, const int* H, const int* W,
+                     const float* const* selw, const float* const* selb, const int* Co, const float* centres, int N,
+                     float* emb, int align_corners, deft_stream_t s) {
+    DEFT_REQUIRE(maps && pitch && C && H && W && selw && selb && Co && centres && emb && N > 0, "afe_extract: bad args");
+    AfeArgs a{};
+    int off = 0;
+    for (int k = 0; k < DEFT_AFE_MAPS; ++k) {
+        DEFT_REQUIRE(maps[k] && selw[k] && selb[k] && C[k] % 4 == 0 && C[k] <= 512 && Co[k] <= 64 && pitch[k] % 4 == 0,
+                     "afe_extract: map %d needs C%%4==0, C<=512, Co<=64", k);
+        a.map[k] = maps[k]; a.w[k] = selw[k]; a.b[k] = selb[k];
+        a.pitch[k] = pitch[k]; a.C[k] = C[k]; a.H[k] = H[k]; a.W[k] = W[k]; a.Co[k] = Co[k]; a.off[k] = off;
+        off += Co[k];
+    }
+    a.Cemb = off;
+    a.align_corners = align_corners;
+    afe_extract_kernel<<<dim3(N, DEFT_AFE_MAPS), 256, 0, to_stream(s)>>>(a, centres, emb);
+    DEFT_CHECK_LAUNCH("afe_extract");
+    return DEFT_OK;
+}
+
+static void affinity_ws_layout(int F, int P, size_t* o_au, size_t* o_bv, size_t* o_h2, size_t* o_h3, size_t* o_h4, size_t* o_s, size_t* total) {
+    size_t pairs = (size_t)F * P * P, off = 0;
+    *o_au = off; off += align_up((size_t)F * P * 512 * 4, 256);
+    *o_bv = off; off += align_up((size_t)P * 512 * 4, 256);
+    *o_h2 = off; off += align_up(pairs * 256 * 4, 256);
+    *o_h3 = off; off += align_up(pairs * 128 * 4, 256);
+    *o_h4 = off; off += align_up(pairs * 64 * 4, 256);
+    *o_s = off; off += align_up(pairs * 4, 256);
+    *total = off;
+}
+
+size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb) {
+    (void)Cemb;
+    size_t a, b, c, d, e, f, t;
+    affinity_ws_layout(F, P, &a, &b, &c, &d, &e, &f, &t);
+    return t;
+}
+
+static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, int ldw, const float* sc, const float* sh,
+                      float* out, int ldo, int Cout, int relu, unsigned flags, cudaStream_t st) {
+    ConvAP ap{};
+    ap.nsrc = 1; ap.Ctot = K; ap.src[0] = A; ap.c[0] = K; ap.pitch[0] = lda;
+    ap.N = 1; ap.H = 1; ap.W = Mrows; ap.OH = 1; ap.OW = Mrows; ap.KH = 1; ap.KW = 1; ap.stride = 1; ap.pad = 0;
+    Epilogue ep{sc, sh, nullptr, 0, out, ldo, Cout, relu};
+    if (flags & DEFT_FLAG_TENSORCORE) {
+        int rc = tc_conv_dispatch(ap, Wp, ldw, K, Mrows, ep, flags, st);
+        if (rc != DEFT_EINVAL) return rc;
+    }
+    return launch_igemm(ap, Wp, ldw, K, Mrows, ep, st);
+}
+
+int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb, const float* w1a,
+                      const float* w1b, const float* sh1, const float* w2, const float* sc2, const float* sh2, const float* w3,
+                      const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5, float* out,
+                      unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
+    DEFT_REQUIRE(xp && n_host && xn && out && ws && w1a && w1b && sh1 && w2 && w3 && w4 && w5, "afe_affinity: null argument");
+    DEFT_REQUIRE(F >= 1 && F <= AFF_MAX_FRAMES && m >= 1 && m <= P && P <= 1024 && Cemb % 16 == 0,
+                 "afe_affinity: need 1<=F<=%d, 1<=m<=P<=1024, Cemb%%16==0", AFF_MAX_FRAMES);
+    size_t o_au, o_bv, o_h2, o_h3, o_h4, o_s, total;
+    affinity_ws_layout(F, P, &o_au, &o_bv, &o_h2, &o_h3, &o_h4, &o_s, &total);
+    if (ws_bytes < total) { set_error("afe_affinity: workspace too small"); return DEFT_EWORKSPACE; }
+    char* base = reinterpret_cast<char*>(ws);
+    float* au = (float*)(base + o_au); float* bv = (float*)(base + o_bv); float* h2 = (float*)(base + o_h2);
+    float* h3 = (float*)(base + o_h3); float* h4 = (float*)(base + o_h4); float* S = (float*)(base + o_s);
+    cudaStream_t st = to_stream(s);
+    PairAP pap{};
+    SoftmaxArgs sa{};
+    int M = 0;
+    for (int f = 0; f < F; ++f) {
+        DEFT_REQUIRE(n_host[f] >= 0 && n_host[f] <= P, "afe_affinity: n[%d]=%d out of range", f, n_host[f]);
+        pap.off[f] = M; sa.off[f] = M; sa.n[f] = n_host[f];
+        M += n_host[f] * m;
+    }
+    pap.off[F] = M; sa.off[F] = M;
+    if (M == 0) return DEFT_OK;
+    int rc;
+    // layer 1, decomposed: Au' = bnfold(W1a u_i + b1), Bv' = bnfold-scale(W1b v_j)
+    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    // layer 2 with the pair expansion relu(Au'_i + Bv'_j) as the A producer
+    pap.au = au; pap.bv = bv; pap.P = P; pap.m = m; pap.F = F; pap.ld = 512;
+    Epilogue e2{sc2, sh2, nullptr, 0, h2, 256, 256, 1};
+    if ((rc = launch_igemm(pap, w2, 256, 512, M, e2, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h2, 256, M, 256, w3, 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h3, 128, M, 128, w4, 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
+    affinity_final_kernel<<<ceil_div(M, 32), 256, 0, st>>>(h4, w5, b5, S, M);
+    DEFT_CHECK_LAUNCH("affinity_final");
+    sa.m = m; sa.P = P;
+    affinity_softmax_kernel<<<F, 256, 4 * P * sizeof(float), st>>>(S, sa, out);
+    DEFT_CHECK_LAUNCH("affinity_softmax");
+    return DEFT_OK;
+}
+
+int deft_lstm_step(const float* x, const float* h, const float* c, const float* w_ih, const float* w_hh, const float* b_ih,
+                   const float* b_hh, const float* w1, const float* b1, const float* w2, const float* b2, int T, int F, int nout,
+                   float* h_out, float* c_out, float* pred, deft_stream_t s) {
+    DEFT_REQUIRE(x && h && c && w_ih && w_hh && b_ih && b_hh && w1 && b1 && w2 && b2 && h_out && c_out && pred, "lstm_step: null argument");
+    DEFT_REQUIRE(T >= 1 && F >= 1 && F <= 32 && nout >= 1 && nout <= 64, "lstm_step: need F<=32, nout<=64 (F=%d nout=%d)", F, nout);
+    lstm_step_kernel<<<T, 128, 0, to_stream(s)>>>(x, h, c, w_ih, w_hh, b_ih, b_hh, w1, b1, w2, b2, F, nout, h_out, c_out, pred);
+    DEFT_CHECK_LAUNCH("lstm_step");
+    return DEFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+/* deft_b200 -- C ABI of the B200-native DEFT per-frame dense hot path (libdeft_b200.so).
+ *
+ * The reference (MedChaabane/DEFT) has no FFI of its own: its boundary is the Python surface of
+ * src/lib/model (+ the external dcn_v2 extension + kalman_filter_lstm).  Every entry point below
+ * names the reference interface it replaces (file:line relative to /root/reference/src/lib);
+ * deft_b200/ (Python) re-exposes them under the reference's own class/function names and
+ * INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 = DEFT_E*; deft_last_error() gives the message of
+ *     the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; fp32 everywhere, int64 indices.
+ *   - activations are NHWC ("channels-last": element (n,y,x,c) at ((n*H+y)*W+x)*pitch + c, where
+ *     pitch >= C lets a tensor live inside a wider concat buffer).  deft_nchw_to_nhwc /
+ *     deft_nhwc_to_nchw convert at the reference's NCHW boundary; head outputs are plain NCHW.
+ *   - the library is stream-ordered, never allocates or frees device memory, never synchronises
+ *     the host, keeps no pointer after return (CUDA-graph capturable).  Scratch is caller-owned
+ *     (`ws`, size from the matching *_workspace_bytes()).
+ *   - weights come pre-packed by deft_b200/packing.py (layouts documented per function).
+ */
+#ifndef DEFT_B200_H
+#define DEFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* deft_stream_t; /* cudaStream_t */
+
+#define DEFT_OK 0
+#define DEFT_EINVAL (-1)   /* bad argument / unsupported shape        */
+#define DEFT_ECUDA (-2)    /* CUDA launch/runtime error                */
+#define DEFT_EWORKSPACE (-3) /* workspace too small                    */
+
+#define DEFT_FLAG_RELU 1u
+#define DEFT_FLAG_TENSORCORE 2u   /* use the tcgen05 (3xTF32) engine where available */
+#define DEFT_FLAG_TF32X1 4u       /* single-pass TF32 (faster, ~1e-3 per layer)      */
+
+#define DEFT_MAX_SRC 4
+#define DEFT_MAX_HEADS 12
+#define DEFT_AFE_MAPS 13
+
+int deft_version(void);
+const char* deft_last_error(void);
+/* 1 if the current device is sm_100 (B200); the product path refuses to run elsewhere. */
+int deft_device_ok(void);
+
+/* ---- layout converters at the reference's NCHW boundary ------------------------------------ */
+int deft_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int N, int C, int H, int W, deft_stream_t s);
+int deft_nhwc_to_nchw(const float* src, int src_pitch, float* dst, int N, int C, int H, int W, deft_stream_t s);
+
+/* ---- a2: nn.Conv2d + eval BatchNorm2d (+ residual) (+ ReLU) over a channel-concat of up to 4
+ * sources.  Replaces BasicBlock/Root/project/level convs (dla.py:47-87,184-207,301-398).
+ *   out[p,co] = act( scale[co]*sum_k A[p,k]*Wp[k,co] + shift[co] + residual[p,co] )
+ * Wp packed [KH*KW*Cin_total][ldw], k = (ky*KW+kx)*Cin_total + ci, ldw = Cout rounded up to 16.
+ * Cin of every source must be a multiple of 16.  residual may be NULL. */
+int deft_conv2d_bn_act(const float* const* srcs_host, const int* src_c_host, const int* src_pitch_host, int nsrc,
+                       int N, int H, int W, const float* w_packed, int ldw, const float* scale, const float* shift,
+                       const float* residual, int res_pitch, float* out, int out_pitch, int Cout,
+                       int KH, int KW, int stride, int pad, unsigned flags, deft_stream_t s);
+
+/* ---- a2: the 7x7 stem on the raw NCHW image (dla.py:301-305): x[N,3,H,W] -> NHWC [N,H,W,16].
+ * w_packed [7*7*3][16] (k = (ky*7+kx)*3+ci). */
+int deft_stem_conv7x7(const float* x_nchw, int N, int H, int W, const float* w_packed, const float* scale,
+                      const float* shift, float* out, int out_pitch, deft_stream_t s);
+
+/* ---- a2: nn.MaxPool2d(2,2) (dla.py:262). H, W are the INPUT dims (even). */
+int deft_maxpool2x2(const float* in, int in_pitch, float* out, int out_pitch, int N, int H, int W, int C, deft_stream_t s);
+
+/* ---- a3: dcn_v2.DCN.forward (+ DeformConv's BN/ReLU, dla.py:646-665), i.e. upstream
+ * dcn_v2_forward(input,weight,bias,offset,mask,3,3,1,1,1,1,1,1,1) fused with its conv_offset_mask.
+ *   om = conv3x3(x; w_om)+b_om ; offset=cat(om[0:9],om[9:18]) (chunk order), mask=sigmoid(om[18:27])
+ *   y[p,co] = act( scale[co]*sum_{k,ci} Wp[k*Cin+ci,co]*mask_k(p)*bilinear(x[:,ci]; p+tap_k+off_k(p)) + shift[co] )
+ * (bias and BN are folded into scale/shift by the packer; scale=1, shift=bias gives the bare op).
+ * w_om_packed [9*Cin][32] (27 real columns), b_om[32]; Wp [9*Cin][ldw].
+ * ws: >= deft_dcnv2_workspace_bytes() (holds the [P,32] offset/mask map). */
+size_t deft_dcnv2_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin,
+                       const float* w_om_packed, const float* b_om, const float* w_packed, int ldw,
+                       const float* scale, const float* shift, float* y, int y_pitch, int Cout,
+                       unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
+
+/* ---- a4: IDAUp's depthwise ConvTranspose2d(k=2f,s=f,p=f/2,groups=C) fused with the following
+ * `layers[i] + layers[i-1]` (dla.py:693-699).  x [N,h,w,C] -> out [N,h*f,w*f,C] = up(x) + skip.
+ * w_packed [(2f)*(2f)][C].  skip may be NULL. */
+int deft_upsample_add(const float* x, int x_pitch, const float* w_packed, const float* skip, int skip_pitch,
+                      float* out, int out_pitch, int N, int h, int w, int C, int f, deft_stream_t s);
+
+/* ---- a5: all CenterNet heads at once (base_model.py:33-68,127-131):
+ *   hidden = relu(conv3x3(feat; 64 -> nheads*256) + b1) ; out_h = conv1x1(hidden_h; 256 -> C_h) + b2_h
+ * w1_packed [9*64][nheads*256]; w2 [sum C_h][256] row-major; b2 [sum C_h].
+ * outs_host[h] -> plain NCHW [N,C_h,H,W].  ws holds the hidden map. */
+size_t deft_heads_workspace_bytes(int N, int H, int W, int nheads, int head_conv);
+int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, int Cin,
+                       const float* w1_packed, const float* b1, int head_conv,
+                       const float* w2, const float* b2, const int* head_c_host, int nheads,
+                       float* const* outs_host, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
+
+/* ---- a6: Detector._sigmoid_output (detector.py:486-494), in place on NCHW heads. dep may be NULL. */
+int deft_sigmoid_output(float* hm, size_t n_hm, float* dep, size_t n_dep, float depth_scale, deft_stream_t s);
+
+/* ---- a6: generic_decode = _nms + _topk + gathers (decode.py:102-219, utils.py:69-104).
+ * hm [B,C,H,W] already sigmoided.  reg/wh/ltrb_amodal NCHW or NULL.
+ * Outputs: scores[B,K] f32, inds[B,K] i64 (y*W+x), clses[B,K] i32, ys/xs[B,K] f32,
+ * bboxes[B,K,4] (from wh; or from ltrb_amodal when given, as the reference overwrites it),
+ * bboxes_amodal[B,K,4] or NULL.  Tie rule among equal scores: lowest flat index first.
+ * K <= 1024. */
+size_t deft_decode_workspace_bytes(int B, int C, int H, int W, int K);
+int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float* reg, const float* wh,
+                const float* ltrb_amodal, float* scores, int64_t* inds, int32_t* clses, float* ys, float* xs,
+                float* bboxes, float* bboxes_amodal, void* ws, size_t ws_bytes, deft_stream_t s);
+/* _tranpose_and_gather_feat (utils.py:32-36): feat [B,C,H,W], inds [B,K] -> out [B,K,C]. */
+int deft_gather_feat(const float* feat, int B, int C, int HW, const int64_t* inds, int K, float* out, deft_stream_t s);
+
+/* ---- a7: AFE_module.forward_feature_extracter (AFE.py:88-92,162-188), evaluated sparsely: the
+ * selector conv3x3+ReLU is computed only at the (up to) 4 bilinear corners of every centre.
+ * maps_host[k] NHWC [1,H_k,W_k,C_k]; selw_host[k] packed [9*C_k][Co_k]; selb_host[k] [Co_k];
+ * centres [N,2] (x,y) in [-1,1] (grid_sample, padding_mode=border); emb [N, sum Co_k]. */
+int deft_afe_extract(const float* const* maps_host, const int* pitch_host, const int* C_host, const int* H_host,
+                     const int* W_host, const float* const* selw_host, const float* const* selb_host,
+                     const int* Co_host, const float* centres, int N, float* emb, int align_corners, deft_stream_t s);
+
+/* ---- a8: AFE_module.forward_stacker_features (AFE.py:110-160) for F memory frames in one call.
+ * xp [F,P,Cemb] (rows >= n_f ignored), n_host[F]; xn [P,Cemb] (m live rows).
+ * Packed MLP (packing.py: stacker2_bn and the three BNs folded):
+ *   w1a,w1b [Cemb][512] + sh1a[512] (all of bias/BN shift), w2 [512][256]+sc2,sh2, w3 [256][128]+sc3,sh3,
+ *   w4 [128][64]+b4, w5[64], b5.
+ * out [F,P,P+1]: out[f,i,j<m] = max(softmax_row, softmax_col)[i,j]; out[f,i,m] = softmax_row[i,P];
+ * rows >= n_f / cols > m untouched.  P = max_object (the softmax denominators contain the
+ * (P-n)/(P-m) zero entries and the constant-1 row/col exactly as the reference). */
+size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb);
+int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb,
+                      const float* w1a, const float* w1b, const float* sh1,
+                      const float* w2, const float* sc2, const float* sh2,
+                      const float* w3, const float* sc3, const float* sh3,
+                      const float* w4, const float* b4, const float* w5, float b5,
+                      float* out, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
+
+/* ---- a10: KalmanFilterLSTM.predict (kalman_filter_lstm.py:65-78) for T independent tracks in one
+ * launch: one LSTM step (gate order i,f,g,o) + out1 (128->64, no activation) + out2 (64->nout).
+ * x [T,F], h/c [T,128] -> h_out/c_out [T,128], pred [T,nout].  Weights in PyTorch layout
+ * (w_ih [512,F], w_hh [512,128], w1 [64,128], w2 [nout,64]). */
+int deft_lstm_step(const float* x, const float* h, const float* c, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, const float* w1, const float* b1, const float* w2,
+                   const float* b2, int T, int F, int nout, float* h_out, float* c_out, float* pred, deft_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFT_B200_H */

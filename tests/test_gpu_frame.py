@@ -1,0 +1,178 @@
+"""GPU parity tests, whole frame: the drop-in DLASeg / AFE / decode / LSTM path against (1) goldens produced
+by the REAL reference modules (tests/golden/frame_*.pt), (2) the CPU oracle at BASELINE config C1
+(512x512, 10x10 affinity), (3) size-independent properties at the full C2 size (1088x608)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, nerr
+from oracle import restate, spec
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # BASELINE.json: 1e-3 relative fp32
+TOL_ANCHOR = 5e-5   # the fp32 SIMT engine
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def build(heads, dataset, dev, max_object=100, **kw):
+    from deft_b200.model.model import create_model
+    from deft_b200.opts import Opt
+    opt = Opt(dataset=dataset, max_object=max_object, heads=dict(heads), **kw)
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt).eval()
+    sd = spec.make_state_dict(spec.dlaseg_spec(heads, dataset=dataset))
+    missing = m.load_state_dict(sd, strict=True)
+    return m.to(dev), sd, opt
+
+
+FRAMES = [("frame_mot_96x128", spec.MOT_HEADS, "mot"), ("frame_kitti_64x160", spec.KITTI_HEADS, "kitti"),
+          ("frame_nusc_64x96", spec.NUSC_HEADS, "nuscenes")]
+
+
+@pytest.mark.parametrize("tensor_core", [False, True], ids=["simt", "tc3x"])
+@pytest.mark.parametrize("name,heads,dataset", FRAMES)
+def test_frame_vs_reference_golden(dev, name, heads, dataset, tensor_core):
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    mt = g["meta"]
+    m, sd, opt = build(heads, dataset, dev, max_object=mt["max_object"], tensor_core=tensor_core)
+    tol = TOL if tensor_core else TOL_ANCHOR
+    x = spec.make_input((1, 3, mt["H"], mt["W"]), tag="image").to(dev)
+    out, fm = m(x)
+    assert isinstance(out, list) and len(out) == 1 and list(out[0].keys()) == list(heads.keys())
+    errs = {}
+    for h in heads:
+        assert out[0][h].shape == g["heads"][h].shape
+        errs[h] = nerr(out[0][h].cpu(), g["heads"][h])
+    assert len(fm) == 13
+    for i, (f, d) in enumerate(zip(fm, g["fm"])):
+        assert list(f.shape) == d["shape"], i
+        fc = f.contiguous().cpu().view(-1)
+        errs[f"fm{i}"] = nerr(fc[d["pos"]], d["val"])
+        assert abs(float(fc.double().abs().sum()) - d["abssum"]) / d["abssum"] < 1e-3
+    centres = spec.make_uniform((1, mt["N"], 1, 1, 2), -1.05, 1.05, tag="centres").to(dev)
+    centres_prev = spec.make_uniform((1, mt["n_prev"], 1, 1, 2), -1.0, 1.0, tag="centres_prev").to(dev)
+    emb = m.AFE.forward_feature_extracter(fm, centres)
+    emb_prev = m.AFE.forward_feature_extracter(fm, centres_prev)
+    errs["emb"] = nerr(emb.cpu(), g["emb"])
+    errs["emb_prev"] = nerr(emb_prev.cpu(), g["emb_prev"])
+    errs["aff"] = nerr(m.AFE.forward_stacker_features(emb_prev, emb, False), g["aff"])
+    errs["aff_fill"] = nerr(m.AFE.forward_stacker_features(emb_prev, emb, True), g["aff_fill"])
+    print(name, "tc" if tensor_core else "simt", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+    # decode on OUR heads: same detections as the reference's decode on ITS heads wherever the score gap
+    # to the next candidate exceeds the network tolerance (hard part 4)
+    from deft_b200.model.decode import generic_decode, sigmoid_output
+    dec = generic_decode(sigmoid_output({k: v.clone() for k, v in out[0].items()}, opt), K=mt["K"], opt=opt)
+    ref = g["decode"]
+    assert nerr(dec["scores"].cpu(), ref["scores"]) < 5 * tol
+    gaps = (ref["scores"][0, :-1] - ref["scores"][0, 1:]).abs()
+    stable = torch.ones(mt["K"], dtype=torch.bool)
+    stable[:-1] &= gaps > 1e-4
+    stable[1:] &= gaps > 1e-4
+    stable[-1] = False
+    assert torch.equal(dec["xs"].cpu()[0][stable], ref["xs"][0][stable])
+    assert torch.equal(dec["ys"].cpu()[0][stable], ref["ys"][0][stable])
+    assert torch.equal(dec["clses"].cpu()[0][stable], ref["clses"][0][stable])
+
+
+@pytest.mark.parametrize("tensor_core", [False, True], ids=["simt", "tc3x"])
+def test_c1_512_frame_vs_oracle(dev, tensor_core):
+    """BASELINE config C1: 512x512 frame, DLA-34+DCNv2 forward + 10x10 affinity, CPU oracle vs B200."""
+    heads = spec.MOT_HEADS
+    m, sd, opt = build(heads, "mot", dev, tensor_core=tensor_core)
+    tol = TOL if tensor_core else TOL_ANCHOR
+    x = spec.make_input((1, 3, 512, 512), tag="c1")
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        ref_out, ref_fm = restate.dlaseg_forward(sd, x, heads)
+    out, fm = m(x.to(dev))
+    errs = {h: nerr(out[0][h].cpu(), ref_out[0][h]) for h in heads}
+    for i in range(13):
+        errs[f"fm{i}"] = nerr(fm[i].cpu(), ref_fm[i])
+    centres = spec.make_uniform((1, 10, 1, 1, 2), -1, 1, tag="c1c")
+    centres_prev = spec.make_uniform((1, 10, 1, 1, 2), -1, 1, tag="c1p")
+    with torch.no_grad():
+        e_ref = restate.afe_extract(sd, ref_fm, centres)
+        p_ref = restate.afe_extract(sd, ref_fm, centres_prev)
+        a_ref = restate.afe_affinity(sd, p_ref, e_ref, 100, False)
+    e = m.AFE.forward_feature_extracter(fm, centres.to(dev))
+    p = m.AFE.forward_feature_extracter(fm, centres_prev.to(dev))
+    a = m.AFE.forward_stacker_features(p, e, False)
+    errs["emb"] = nerr(e.cpu(), e_ref)
+    errs["aff"] = nerr(a, a_ref)
+    assert a.shape == (10, 11)
+    print("C1", "tc" if tensor_core else "simt", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
+    # decode on the ORACLE's heat-map, shared tensor: bit-exact
+    from deft_b200.model.decode import generic_decode
+    sig = restate.sigmoid_output(ref_out[0])
+    dref = restate.generic_decode(sig, K=100)
+    dgpu = generic_decode({k: v.to(dev) for k, v in sig.items()}, K=100, opt=opt)
+    for k in ("scores", "clses", "xs", "ys", "bboxes", "tracking"):
+        assert torch.equal(dgpu[k].cpu(), dref[k]), k
+
+
+def test_c2_full_size_properties(dev):
+    """1088x608 (BASELINE C2), where the CPU oracle is too slow for the test suite: size-independent properties.
+    (1) CUDA graph replay == eager launch list, bit for bit; (2) determinism; (3) FeatureMaps idx9 is idx5,
+    idx10 equals idx6 (dla.py:792-799); (4) decode output sorted, idempotent NMS; (5) affinity rows are
+    probabilities; (6) DCN linearity in the weights on a full-size layer."""
+    heads = spec.MOT_HEADS
+    m, sd, opt = build(heads, "mot", dev)
+    x = spec.make_input((1, 3, 608, 1088), tag="c2").to(dev)
+    out, fm = m(x)
+    h1 = {k: v.clone() for k, v in out[0].items()}
+    f1 = [f.clone() for f in fm]
+    shapes = [(16, 608, 1088), (32, 304, 544), (64, 152, 272), (128, 76, 136), (256, 38, 68), (512, 19, 34), (64, 152, 272),
+              (128, 76, 136), (256, 38, 68), (512, 19, 34), (64, 152, 272), (64, 152, 272), (64, 152, 272)]
+    assert [tuple(f.shape[1:]) for f in fm] == shapes
+    assert torch.equal(f1[9], f1[5]) and torch.equal(f1[10], f1[6])
+    for f in f1:
+        assert torch.isfinite(f).all()
+    m.use_cuda_graph = True
+    m.invalidate()
+    out2, fm2 = m(x)
+    out2, fm2 = m(x)
+    for k in h1:
+        assert torch.equal(out2[0][k], h1[k]), k
+    for a, b in zip(fm2, f1):
+        assert torch.equal(a, b)
+    from deft_b200.model.decode import generic_decode, sigmoid_output
+    o = sigmoid_output({k: v.clone() for k, v in h1.items()}, opt)
+    dec = generic_decode(o, K=100, opt=opt)
+    s = dec["scores"][0]
+    assert (s[:-1] >= s[1:]).all() and (s > 0).all()
+    flat = dec["ys"][0].long() * 272 + dec["xs"][0].long()
+    assert flat.unique().numel() == 100
+    assert torch.equal(o["hm"].view(-1)[flat], s)                     # scores are the heat values at the peaks
+    centres = torch.stack([dec["xs"][0] / 272 * 2 - 1, dec["ys"][0] / 152 * 2 - 1], 1).view(1, 100, 1, 1, 2)
+    emb = m.AFE.forward_feature_extracter(fm, centres)
+    assert emb.shape == (1, 100, 416) and torch.isfinite(emb).all() and (emb >= 0).all()
+    mem = torch.stack([emb[0] * (1 + 0.01 * f) for f in range(5)])   # 5 memory frames x 100 = 500 track embeddings
+    aff = m.AFE.affinity_batched(mem.contiguous(), [100] * 5, emb[0].contiguous())
+    assert aff.shape == (5, 100, 101)
+    assert (aff >= 0).all() and (aff <= 1).all()
+    # same-frame self affinity must differ from a perturbed memory frame (the MLP sees the memory)
+    assert not torch.equal(aff[0], aff[4])
+    # DCN linearity in W on the biggest DCN layer shape (64->64 @152x272)
+    from deft_b200 import ops, packing
+    sp = {}
+    spec._deform(sp, "d", 64, 64)
+    s1 = {k: v.to(dev) for k, v in spec.make_state_dict(sp, seed=1).items()}
+    s2 = dict(s1)
+    s2["d.conv.weight"] = spec.make_state_dict(sp, seed=2)["d.conv.weight"].to(dev)
+    s3 = dict(s1)
+    s3["d.conv.weight"] = s1["d.conv.weight"] + s2["d.conv.weight"]
+    xin = ops.as_nhwc(f1[12])
+    ys = [ops.dcnv2_forward(xin, packing.pack_dcn(s, "d.conv"), relu=False).nchw_view() for s in (s1, s2, s3)]
+    bias = s1["d.conv.bias"].view(1, -1, 1, 1)
+    assert nerr((ys[0] + ys[1] - bias).cpu(), ys[2].cpu()) < 1e-5

@@ -1,0 +1,112 @@
+"""CPU suite, part 2: host logic without a GPU -- the C-ABI library loads and exports every symbol
+include/deft_b200.h declares, the drop-in modules carry the reference's state_dict, weight packing is
+algebraically right, and the product path fails loudly on CPU tensors (no fallback)."""
+import json
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, ROOT, nerr
+from oracle import restate, spec
+
+
+def test_library_exports_every_declared_symbol():
+    from deft_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "deft_b200.h")).read()
+    declared = set(re.findall(r"\b(deft_[a-z0-9_]+)\s*\(", hdr))
+    l = _lib.lib()                      # raises if the .so is missing
+    for name in declared:
+        assert hasattr(l, name), name
+    assert declared == set(_lib.exported_symbols())
+    assert l.deft_version() >= 100
+
+
+@pytest.mark.parametrize("heads,dataset", [(spec.MOT_HEADS, "mot"), (spec.KITTI_HEADS, "kitti"), (spec.NUSC_HEADS, "nuscenes")])
+def test_dropin_state_dict_matches_reference(heads, dataset):
+    from deft_b200.model.model import create_model
+    from deft_b200.opts import Opt
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, Opt(dataset=dataset, heads=dict(heads)))
+    with open(os.path.join(GOLDEN, f"state_dict_keys_{dataset}_{len(heads)}heads.json")) as f:
+        ref = {k: tuple(v) for k, v in json.load(f).items()}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
+    m.load_state_dict(spec.make_state_dict(spec.dlaseg_spec(heads, dataset=dataset)), strict=True)
+
+
+def test_checkpoint_with_pre_img_layers_and_module_prefix(tmp_path):
+    """Real DEFT checkpoints carry base.pre_img_layer/pre_hm_layer and may be 'module.'-prefixed (model.py:48-52)."""
+    from deft_b200.model.model import create_model, load_model, save_model
+    from deft_b200.opts import Opt
+    heads = spec.MOT_HEADS
+    sd = spec.make_state_dict(spec.dlaseg_spec(heads, pre_img=True, pre_hm=True))
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"epoch": 7, "state_dict": {"module." + k: v for k, v in sd.items()}}, path)
+    opt = Opt(pre_img=True, pre_hm=True)
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt)
+    m = load_model(m, path, opt)
+    got = m.state_dict()
+    assert set(got) == set(sd)
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    save_model(str(tmp_path / "out.pth"), 8, m)
+    assert set(torch.load(str(tmp_path / "out.pth"), weights_only=False)["state_dict"]) == set(sd)
+    m2 = create_model("dla_34", dict(heads), {h: [256] for h in heads}, Opt())   # without the dead layers: they are dropped
+    load_model(m2, path, Opt())
+
+
+def test_no_cpu_fallback():
+    from deft_b200._lib import DeftError
+    from deft_b200.kalman_filter_lstm import DecoderRNN
+    from deft_b200.model.decode import generic_decode
+    from deft_b200.model.model import create_model
+    from deft_b200.opts import Opt
+    heads = spec.MOT_HEADS
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, Opt()).eval()
+    with pytest.raises(DeftError):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(DeftError):
+        m.AFE.forward_feature_extracter([torch.zeros(1, 16, 8, 8)] * 13, torch.zeros(1, 2, 1, 1, 2))
+    with pytest.raises(DeftError):
+        m.AFE.forward_stacker_features(torch.zeros(1, 2, 416), torch.zeros(1, 2, 416))
+    with pytest.raises(DeftError):
+        generic_decode({"hm": torch.zeros(1, 1, 8, 8)}, K=4)
+    with pytest.raises(DeftError):
+        DecoderRNN(128, "mot").step(torch.zeros(1, 11), torch.zeros(1, 128), torch.zeros(1, 128))
+    with pytest.raises(NotImplementedError):
+        create_model("resdcn_18", dict(heads), {h: [256] for h in heads}, Opt())
+
+
+def test_product_never_imports_oracle():
+    for dp, _, fs in os.walk(os.path.join(ROOT, "deft_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+\.*oracle", src, re.M), os.path.join(dp, f)
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def test_packing_algebra():
+    """pack_conv / fold_bn / pack_affinity reproduce the unfolded arithmetic (CPU, fp32)."""
+    from deft_b200 import packing
+    g = torch.Generator(); g.manual_seed(1)
+    w = torch.randn(24, 16, 3, 3, generator=g)
+    wp, ldw = packing.pack_conv(w)
+    assert ldw == 32 and wp.shape == (144, 32) and torch.equal(wp[:, 24:], torch.zeros(144, 8))
+    x = torch.randn(1, 16, 5, 6, generator=g)
+    cols = F.unfold(x, 3, padding=1).view(16, 9, 30).permute(1, 0, 2).reshape(144, 30)     # k = tap*Cin + ci
+    assert nerr(wp[:, :24].t() @ cols, F.conv2d(x, w, padding=1).view(24, 30)) < 1e-5
+    sd = spec.make_state_dict({k: v for k, v in spec.dlaseg_spec(spec.MOT_HEADS).items() if k.startswith("AFE.")})
+    pk = packing.pack_affinity({k[4:]: v for k, v in sd.items()})
+    xp, xn = spec.make_input((1, 4, 416), tag="pa").abs(), spec.make_input((1, 3, 416), tag="pb").abs()
+    au = xp[0] @ pk["w1a"] + pk["sh1"]
+    bv = xn[0] @ pk["w1b"]
+    h = torch.relu(au[:, None, :] + bv[None, :, :]).reshape(12, 512)
+    h = torch.relu((h @ pk["w2"]) * pk["sc2"] + pk["sh2"])
+    h = torch.relu((h @ pk["w3"]) * pk["sc3"] + pk["sh3"])
+    h = torch.relu(h @ pk["w4"] + pk["b4"])
+    S = torch.relu(h @ pk["w5"] + pk["b5"]).view(4, 3)
+    ref = restate.afe_affinity(sd, xp, xn, 100, False)
+    X = torch.zeros(101, 101); X[:4, :3] = S; X[100, :] = 1; X[:, 100] = 1
+    mine = torch.max(torch.softmax(X, 1), torch.softmax(X, 0))[:4, :3]
+    assert nerr(mine, ref[:, :3]) < 1e-5
