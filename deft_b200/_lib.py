@@ -37,6 +37,7 @@ _SIGS = {
     "deft_decode": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                               c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
     "deft_gather_feat": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
+    "deft_boxes_to_centres": (C.c_int, [c_fp, C.c_int, C.c_float, C.c_float, c_fp, c_fp]),
     "deft_afe_extract": (C.c_int, [c_ptr_p, c_int_p, c_int_p, c_int_p, c_int_p, c_ptr_p, c_ptr_p, c_int_p, c_fp, C.c_int, c_fp,
                                    C.c_int, c_fp]),
     "deft_afe_affinity_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -196,6 +196,15 @@ __global__ void gather_feat_kernel(const float* __restrict__ feat, int C, int HW
     out[i] = feat[((size_t)b * C + c) * HW + inds[(size_t)b * K + k]];
 }
 
+__global__ void boxes_to_centres_kernel(const float* __restrict__ b, int N, float W, float H, float* __restrict__ c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    // convert_detection: w = x2-x1; x1/=W; w/=W; c = 2*x1 + w - 1
+    float x1 = b[i * 4 + 0], y1 = b[i * 4 + 1], x2 = b[i * 4 + 2], y2 = b[i * 4 + 3];
+    c[i * 2 + 0] = (2.f * (x1 / W) + (x2 - x1) / W) - 1.0f;
+    c[i * 2 + 1] = (2.f * (y1 / H) + (y2 - y1) / H) - 1.0f;
+}
+
 // ================================================================================================
 // a7: AFE sparse extractor.  grid (N, 13), 256 threads: thread = (corner 0..3, out channel 0..63).
 struct AfeArgs {
@@ -438,6 +447,13 @@ int deft_gather_feat(const float* feat, int B, int C, int HW, const int64_t* ind
     int total = B * K * C;
     gather_feat_kernel<<<ceil_div(total, 256), 256, 0, to_stream(s)>>>(feat, C, HW, (const long long*)inds, K, out, total);
     DEFT_CHECK_LAUNCH("gather_feat");
+    return DEFT_OK;
+}
+
+int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* centres, deft_stream_t s) {
+    DEFT_REQUIRE(boxes && centres && N > 0 && W > 0 && H > 0, "boxes_to_centres: bad args");
+    boxes_to_centres_kernel<<<ceil_div(N, 128), 128, 0, to_stream(s)>>>(boxes, N, W, H, centres);
+    DEFT_CHECK_LAUNCH("boxes_to_centres");
     return DEFT_OK;
 }
 

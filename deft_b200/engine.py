@@ -166,6 +166,22 @@ class FramePlan:
             if rc != 0:
                 _lib.check(rc, name)
 
+    def launch_profiled(self):
+        """Eager launch with a CUDA-event pair around every C-ABI call (on the launching stream).
+        Returns [(entry point, milliseconds)], used by bench.py for the per-kernel roofline."""
+        s = _lib.stream_ptr()
+        evs = []
+        for fn, args, name in self.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args, s)
+            e1.record()
+            if rc != 0:
+                _lib.check(rc, name)
+            evs.append((name, args, e0, e1))
+        torch.cuda.synchronize(self.device)
+        return [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in evs]
+
     def run(self, x):
         if x.data_ptr() != self.x_in.data_ptr():
             self.x_in.copy_(x, non_blocking=True)

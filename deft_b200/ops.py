@@ -170,6 +170,15 @@ def gather_feat(feat, inds):
     return out
 
 
+def boxes_to_centres(boxes, W, H, out=None):
+    """boxes [N,4] device (x1,y1,x2,y2) in a WxH frame -> [N,2] centres in [-1,1] (image.py:391-412)."""
+    N = boxes.shape[0]
+    if out is None:
+        out = torch.empty((N, 2), dtype=torch.float32, device=boxes.device)
+    check(lib().deft_boxes_to_centres(boxes.data_ptr(), N, C.c_float(W), C.c_float(H), out.data_ptr(), stream_ptr()), "boxes_to_centres")
+    return out
+
+
 def afe_extract(maps, sel_w, sel_b, sel_co, centres, align_corners=False, out=None):
     """maps: 13 NHWC handles (batch 1); centres [N,2] device tensor -> emb [N, Cemb]."""
     N = centres.shape[0]

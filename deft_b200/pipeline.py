@@ -1,0 +1,136 @@
+"""Per-stream frame pipeline: the public "one call per frame" API of deft_b200.
+
+Chains, on one CUDA stream with no host synchronisation in between, exactly what the reference does
+per frame between `images.to(device)` and the tracker's cost matrix:
+
+    DLASeg.forward -> _sigmoid_output -> generic_decode(K) -> convert_detection -> AFE extractor (N=K)
+      -> affinity of the K new embeddings against the F-frame embedding memory (FeatureRecorder, tracker.py:46-90)
+      [-> LSTM motion step for T tracks when configured]
+
+and keeps the embedding memory (a ring of F frames x P rows) resident in HBM.  One instance per video
+stream / GPU; streams are independent (no collective), which is how the path shards across GPUs.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .model.decode import _REG_HEADS
+
+KERNELS_PER_CALL = {  # CUDA kernels launched by each C-ABI entry point (for bench.py's gpu_launches)
+    "deft_stem_conv7x7": 1, "deft_conv2d_bn_act": 1, "deft_maxpool2x2": 1, "deft_dcnv2_forward": 2, "deft_upsample_add": 1,
+    "deft_heads_forward": 2, "deft_sigmoid_output": 1, "deft_decode": 3, "deft_gather_feat": 1, "deft_boxes_to_centres": 1,
+    "deft_afe_extract": 1, "deft_afe_affinity": 7, "deft_lstm_step": 1,
+}
+
+
+class FramePipeline:
+    def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True):
+        self.model, self.opt = model, opt
+        self.device = device or next(model.parameters()).device
+        self.H, self.W = height, width
+        self.K = opt.K
+        self.P = opt.max_object
+        if self.K > self.P:
+            raise ValueError("K must be <= max_object (forward_stacker_features contract, AFE.py:110-122)")
+        self.F = mem_frames
+        self.cemb = sum(model.AFE.selector_output_channel)
+        self.lstm, self.T = lstm, lstm_tracks
+        dev = self.device
+        self.x = torch.empty((1, 3, height, width), dtype=torch.float32, device=dev)           # device image slot
+        self.memory = torch.zeros((self.F, self.P, self.cemb), dtype=torch.float32, device=dev)  # embedding ring
+        self.counts = [self.K] * self.F          # live rows per memory frame (steady state: K detections/frame)
+        self.head = 0
+        self.aff = torch.zeros((self.F, self.P, self.P + 1), dtype=torch.float32, device=dev)
+        self.aff_ws = torch.empty(_lib.lib().deft_afe_affinity_workspace_bytes(self.F, self.P, self.cemb), dtype=torch.uint8, device=dev)
+        self.dec_ws = None
+        if lstm is not None:
+            fin = lstm.model.fin
+            self.lstm_h = torch.zeros((self.T, 128), device=dev)
+            self.lstm_c = torch.zeros((self.T, 128), device=dev)
+            self.lstm_x = torch.zeros((self.T, fin), device=dev)
+        self.plan = model.plan_for(self.x)
+        self.x = self.plan.x_in                   # the plan's static input slot: no extra device copy per frame
+        self.graph = None
+        self.out = None
+        self.use_cuda_graph = use_cuda_graph
+
+    # ------------------------------------------------------------------------------------------
+    def _body(self):
+        """Everything after the image is in self.x; returns the dict of device results."""
+        heads, fms = self.plan.run(self.x)
+        hm = heads["hm"]
+        ops.sigmoid_output_(hm, heads.get("dep"), getattr(self.opt, "depth_scale", 1.0))
+        if self.dec_ws is None:
+            B, C, h, w = hm.shape
+            self.dec_ws = torch.empty(_lib.lib().deft_decode_workspace_bytes(B, C, h, w, self.K), dtype=torch.uint8, device=self.device)
+        d = ops.decode(hm, self.K, reg=heads.get("reg"), wh=heads.get("wh"), ltrb_amodal=heads.get("ltrb_amodal"), ws=self.dec_ws)
+        res = {"scores": d["scores"], "clses": d["clses"], "bboxes": d["bboxes"], "xs": d["xs"], "ys": d["ys"]}
+        for h in _REG_HEADS:
+            if h in heads:
+                res[h] = ops.gather_feat(heads[h], d["inds"])
+        oh, ow = hm.shape[2], hm.shape[3]
+        centres = ops.boxes_to_centres(d["bboxes"].view(-1, 4), float(ow), float(oh))
+        pk = self.model.AFE.packed()
+        emb = ops.afe_extract(self.plan.feature_maps, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres, self.model.AFE.align_corners)
+        ops.afe_affinity(self.memory, self.counts, emb, self.K, self.P, pk["mlp"], out=self.aff, ws=self.aff_ws, flags=self.model.AFE._flags)
+        res["embeddings"] = emb
+        res["affinity"] = self.aff
+        if self.lstm is not None:
+            hn, cn, pred = self.lstm.predict_batch(self.lstm_h, self.lstm_c, self.lstm_x)
+            self.lstm_h.copy_(hn)
+            self.lstm_c.copy_(cn)
+            res["lstm_pred"] = pred
+        return res
+
+    def _push_memory(self, emb):
+        self.memory[self.head, : self.K].copy_(emb)
+        self.head = (self.head + 1) % self.F
+
+    def warmup(self):
+        res = self._body()
+        torch.cuda.synchronize(self.device)
+        if self.use_cuda_graph and self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            with torch.cuda.graph(g):
+                self.out = self._body()
+            self.graph = g
+        return res
+
+    def step_device(self, image_dev=None):
+        """One frame with the image already in HBM (copied into the pipeline's slot if given)."""
+        if image_dev is not None and image_dev.data_ptr() != self.x.data_ptr():
+            self.x.copy_(image_dev, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            res = self.out
+        else:
+            res = self._body()
+        self._push_memory(res["embeddings"])
+        return res
+
+    def step(self, image_host, out_host=None):
+        """End-to-end frame through the public API: pinned host image in, host results out
+        (H2D of the frame, D2H of detections + affinity -- the copies the reference makes at
+        detector.py:150,545-547 and AFE.py:154-158)."""
+        self.x.copy_(image_host, non_blocking=True)
+        res = self.step_device()
+        if out_host is None:
+            out_host = {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in ("scores", "clses", "bboxes", "affinity")}
+        for k, v in out_host.items():
+            v.copy_(res[k], non_blocking=True)
+        return out_host
+
+    def count_launches(self):
+        """Kernel launches of one frame (our kernels only), by wrapping the C-ABI table once."""
+        n = self.plan.n_launches
+        n += sum(KERNELS_PER_CALL[k] for k in ("deft_sigmoid_output", "deft_decode", "deft_boxes_to_centres", "deft_afe_extract", "deft_afe_affinity"))
+        n += sum(1 for h in _REG_HEADS if h in self.model.heads)
+        if self.lstm is not None:
+            n += 1
+        return n

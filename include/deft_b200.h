@@ -115,6 +115,10 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
 /* _tranpose_and_gather_feat (utils.py:32-36): feat [B,C,H,W], inds [B,K] -> out [B,K,C]. */
 int deft_gather_feat(const float* feat, int B, int C, int HW, const int64_t* inds, int K, float* out, deft_stream_t s);
 
+/* ---- boundary shim: utils/image.py:391-412 convert_detection on the device.
+ * boxes [N,4] (x1,y1,x2,y2) in a W x H pixel frame -> centres [N,2] = (x1+x2)/W - 1, (y1+y2)/H - 1. */
+int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* centres, deft_stream_t s);
+
 /* ---- a7: AFE_module.forward_feature_extracter (AFE.py:88-92,162-188), evaluated sparsely: the
  * selector conv3x3+ReLU is computed only at the (up to) 4 bilinear corners of every centre.
  * maps_host[k] NHWC [1,H_k,W_k,C_k]; selw_host[k] packed [9*C_k][Co_k]; selb_host[k] [Co_k];
