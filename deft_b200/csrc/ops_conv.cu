@@ -208,6 +208,21 @@ using namespace deft;
 
 extern "C" {
 
+int deft_tc_tile_n(int ldw, int for_dcn) {
+    int bn = tc_tile_n(ldw);
+    return (for_dcn && bn > 64) ? 64 : bn;
+}
+
+size_t deft_tc_blob_bytes(int ldw, int K, int for_dcn) {
+    if (ldw <= 0 || ldw % 16 != 0 || K <= 0) return 0;
+    return align_up(tc_blob_floats(ldw, K, deft_tc_tile_n(ldw, for_dcn)) * sizeof(float), 256);
+}
+
+int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int for_dcn, float* blob, deft_stream_t s) {
+    DEFT_REQUIRE(w_packed && blob && ldw > 0 && ldw % 16 == 0 && K > 0, "tc_pack_weights: bad args");
+    return tc_pack_weights(w_packed, ldw, K, deft_tc_tile_n(ldw, for_dcn), blob, to_stream(s));
+}
+
 int deft_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int N, int C, int H, int W, deft_stream_t s) {
     DEFT_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && dst_pitch >= C, "nchw_to_nhwc: bad args");
     dim3 grid(ceil_div(H * W, 32), ceil_div(C, 32), N), block(32, 8);
@@ -225,8 +240,8 @@ int deft_nhwc_to_nchw(const float* src, int src_pitch, float* dst, int N, int C,
 }
 
 int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* src_pitch, int nsrc, int N, int H, int W,
-                       const float* w_packed, int ldw, const float* scale, const float* shift, const float* residual,
-                       int res_pitch, float* out, int out_pitch, int Cout, int KH, int KW, int stride, int pad,
+                       const float* w_packed, int ldw, const float* w_tc, const float* scale, const float* shift,
+                       const float* residual, int res_pitch, float* out, int out_pitch, int Cout, int KH, int KW, int stride, int pad,
                        unsigned flags, deft_stream_t s) {
     DEFT_REQUIRE(srcs && src_c && src_pitch && nsrc >= 1 && nsrc <= DEFT_MAX_SRC, "conv2d: nsrc must be 1..%d", DEFT_MAX_SRC);
     DEFT_REQUIRE(w_packed && out && N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && stride > 0, "conv2d: bad args");
@@ -249,7 +264,7 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
     int M = N * ap.OH * ap.OW;
     int K = KH * KW * ap.Ctot;
     if (flags & DEFT_FLAG_TENSORCORE) {
-        int rc = tc_conv_dispatch(ap, w_packed, ldw, K, M, ep, flags, to_stream(s));
+        int rc = tc_conv_dispatch(ap, w_tc, ldw, K, M, ep, flags, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;   // EINVAL from the TC engine = shape not covered -> SIMT
     }
     return launch_igemm(ap, w_packed, ldw, K, M, ep, to_stream(s));
@@ -281,7 +296,8 @@ size_t deft_dcnv2_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
 }
 
 int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin, const float* w_om_packed,
-                       const float* b_om, const float* w_packed, int ldw, const float* scale, const float* shift,
+                       const float* b_om, const float* w_om_tc, const float* w_packed, int ldw, const float* w_tc,
+                       const float* scale, const float* shift,
                        float* y, int y_pitch, int Cout, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(x && w_om_packed && b_om && w_packed && y && ws, "dcnv2: null argument");
     DEFT_REQUIRE(Cin % 16 == 0 && x_pitch % 4 == 0 && y_pitch % 4 == 0, "dcnv2: Cin%%16 / pitch%%4 (Cin=%d)", Cin);
@@ -297,7 +313,7 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     cap.N = N; cap.H = H; cap.W = W; cap.OH = H; cap.OW = W; cap.KH = 3; cap.KW = 3; cap.stride = 1; cap.pad = 1;
     Epilogue e1{nullptr, b_om, nullptr, 0, om, 32, 32, 0};
     int rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w_om_packed, 32, 9 * Cin, M, e1, flags & ~DEFT_FLAG_TF32X1, to_stream(s));
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w_om_tc, 32, 9 * Cin, M, e1, flags & ~DEFT_FLAG_TF32X1, to_stream(s));
     if (rc == DEFT_EINVAL) rc = launch_igemm(cap, w_om_packed, 32, 9 * Cin, M, e1, to_stream(s));
     if (rc != DEFT_OK) return rc;
     // 2) deformable gather fused into the GEMM's A producer
@@ -305,7 +321,7 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     dap.x = x; dap.pitch = x_pitch; dap.N = N; dap.H = H; dap.W = W; dap.Cin = Cin; dap.om = om;
     Epilogue e2{scale, shift, nullptr, 0, y, y_pitch, Cout, (flags & DEFT_FLAG_RELU) ? 1 : 0};
     if (flags & DEFT_FLAG_TENSORCORE) {
-        rc = tc_dcn_dispatch(dap, w_packed, ldw, 9 * Cin, M, e2, flags, to_stream(s));
+        rc = tc_dcn_dispatch(dap, w_tc, ldw, 9 * Cin, M, e2, flags, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;
     }
     return launch_igemm(dap, w_packed, ldw, 9 * Cin, M, e2, to_stream(s));
@@ -327,7 +343,7 @@ size_t deft_heads_workspace_bytes(int N, int H, int W, int nheads, int head_conv
     return align_up((size_t)N * H * W * nheads * head_conv * sizeof(float), 256);
 }
 
-int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, int Cin, const float* w1_packed,
+int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, int Cin, const float* w1_packed, const float* w1_tc,
                        const float* b1, int head_conv, const float* w2, const float* b2, const int* head_c, int nheads,
                        float* const* outs, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(feat && w1_packed && b1 && w2 && b2 && head_c && outs && ws, "heads: null argument");
@@ -344,7 +360,7 @@ int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, i
     cap.N = N; cap.H = H; cap.W = W; cap.OH = H; cap.OW = W; cap.KH = 3; cap.KW = 3; cap.stride = 1; cap.pad = 1;
     Epilogue e1{nullptr, b1, nullptr, 0, hidden, HCt, HCt, 1};
     int rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w1_packed, HCt, 9 * Cin, M, e1, flags, to_stream(s));
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w1_tc, HCt, 9 * Cin, M, e1, flags, to_stream(s));
     if (rc == DEFT_EINVAL) rc = launch_igemm(cap, w1_packed, HCt, 9 * Cin, M, e1, to_stream(s));
     if (rc != DEFT_OK) return rc;
     HeadsOut ho{};

@@ -495,14 +495,14 @@ size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb) {
     return t;
 }
 
-static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, int ldw, const float* sc, const float* sh,
+static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, const float* Wtc, int ldw, const float* sc, const float* sh,
                       float* out, int ldo, int Cout, int relu, unsigned flags, cudaStream_t st) {
     ConvAP ap{};
     ap.nsrc = 1; ap.Ctot = K; ap.src[0] = A; ap.c[0] = K; ap.pitch[0] = lda;
     ap.N = 1; ap.H = 1; ap.W = Mrows; ap.OH = 1; ap.OW = Mrows; ap.KH = 1; ap.KW = 1; ap.stride = 1; ap.pad = 0;
     Epilogue ep{sc, sh, nullptr, 0, out, ldo, Cout, relu};
     if (flags & DEFT_FLAG_TENSORCORE) {
-        int rc = tc_conv_dispatch(ap, Wp, ldw, K, Mrows, ep, flags, st);
+        int rc = tc_conv_dispatch(ap, Wtc, ldw, K, Mrows, ep, flags, st);
         if (rc != DEFT_EINVAL) return rc;
     }
     return launch_igemm(ap, Wp, ldw, K, Mrows, ep, st);
@@ -510,7 +510,8 @@ static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp
 
 int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb, const float* w1a,
                       const float* w1b, const float* sh1, const float* w2, const float* sc2, const float* sh2, const float* w3,
-                      const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5, float* out,
+                      const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5,
+                      const float* const* tc, float* out,
                       unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(xp && n_host && xn && out && ws && w1a && w1b && sh1 && w2 && w3 && w4 && w5, "afe_affinity: null argument");
     DEFT_REQUIRE(F >= 1 && F <= AFF_MAX_FRAMES && m >= 1 && m <= P && P <= 1024 && Cemb % 16 == 0,
@@ -534,14 +535,19 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
     if (M == 0) return DEFT_OK;
     int rc;
     // layer 1, decomposed: Au' = bnfold(W1a u_i + b1), Bv' = bnfold-scale(W1b v_j)
-    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    const float* t1a = tc ? tc[0] : nullptr; const float* t1b = tc ? tc[1] : nullptr; const float* t2 = tc ? tc[2] : nullptr;
+    const float* t3 = tc ? tc[3] : nullptr; const float* t4 = tc ? tc[4] : nullptr;
+    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, t1a, 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, t1b, 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
     // layer 2 with the pair expansion relu(Au'_i + Bv'_j) as the A producer
     pap.au = au; pap.bv = bv; pap.P = P; pap.m = m; pap.F = F; pap.ld = 512;
     Epilogue e2{sc2, sh2, nullptr, 0, h2, 256, 256, 1};
-    if ((rc = launch_igemm(pap, w2, 256, 512, M, e2, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h2, 256, M, 256, w3, 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h3, 128, M, 128, w4, 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
+    rc = DEFT_EINVAL;
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_pair_dispatch(pap, t2, 256, 512, M, e2, flags, st);
+    if (rc == DEFT_EINVAL) rc = launch_igemm(pap, w2, 256, 512, M, e2, st);
+    if (rc != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h2, 256, M, 256, w3, t3, 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h3, 128, M, 128, w4, t4, 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
     affinity_final_kernel<<<ceil_div(M, 32), 256, 0, st>>>(h4, w5, b5, S, M);
     DEFT_CHECK_LAUNCH("affinity_final");
     sa.m = m; sa.P = P;

@@ -63,16 +63,26 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, residual=None, out=None, flags=0):
+def tc_pack(wp, ldw, K, for_dcn=False):
+    """Packed weight Wp[K][ldw] -> tcgen05 tile images (device blob); one kernel launch, done at load time."""
+    n = lib().deft_tc_blob_bytes(ldw, K, 1 if for_dcn else 0)
+    blob = torch.empty(n // 4, dtype=torch.float32, device=wp.device)
+    check(lib().deft_tc_pack_weights(wp.data_ptr(), ldw, K, 1 if for_dcn else 0, blob.data_ptr(), stream_ptr()), "tc_pack_weights")
+    return blob
+
+
+def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, residual=None, out=None, flags=0, w_tc=None):
     s0 = srcs[0]
     OH = (s0.H + 2 * pad - kh) // stride + 1
     OW = (s0.W + 2 * pad - kw) // stride + 1
     if out is None:
         out = NHWC.empty(s0.N, OH, OW, cout, s0.t.device)
     fl = flags | (FLAG_RELU if relu else 0)
+    if (flags & FLAG_TENSORCORE) and w_tc is None:
+        w_tc = tc_pack(wp, ldw, wp.shape[0])
     check(lib().deft_conv2d_bn_act(ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
                                    int_array([s.pitch for s in srcs]), len(srcs), s0.N, s0.H, s0.W, wp.data_ptr(), ldw,
-                                   _p(scale), _p(shift), None if residual is None else residual.ptr,
+                                   _p(w_tc), _p(scale), _p(shift), None if residual is None else residual.ptr,
                                    0 if residual is None else residual.pitch, out.ptr, out.pitch, cout, kh, kw, stride, pad,
                                    fl, stream_ptr()), "conv2d_bn_act")
     return out
@@ -105,8 +115,11 @@ def dcnv2_forward(a: NHWC, pk, relu, ws=None, out=None, flags=0):
     if out is None:
         out = NHWC.empty(a.N, a.H, a.W, pk["cout"], a.t.device)
     fl = flags | (FLAG_RELU if relu else 0)
+    if (flags & FLAG_TENSORCORE) and "w_tc" not in pk:
+        pk["w_tc"] = tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], True)
+        pk["w_om_tc"] = tc_pack(pk["w_om"], 32, 9 * pk["cin"], False)
     check(lib().deft_dcnv2_forward(a.ptr, a.pitch, a.N, a.H, a.W, pk["cin"], pk["w_om"].data_ptr(), pk["b_om"].data_ptr(),
-                                   pk["w"].data_ptr(), pk["ldw"], pk["scale"].data_ptr(), pk["shift"].data_ptr(), out.ptr,
+                                   _p(pk.get("w_om_tc")), pk["w"].data_ptr(), pk["ldw"], _p(pk.get("w_tc")), pk["scale"].data_ptr(), pk["shift"].data_ptr(), out.ptr,
                                    out.pitch, pk["cout"], fl, ws.data_ptr(), ws.numel(), stream_ptr()), "dcnv2_forward")
     return out
 
@@ -127,7 +140,9 @@ def heads_forward(feat: NHWC, hp, outs=None, ws=None, flags=0):
                          device=feat.t.device)
     if outs is None:
         outs = [torch.empty((feat.N, c, feat.H, feat.W), dtype=torch.float32, device=feat.t.device) for c in hp["head_c"]]
-    check(lib().deft_heads_forward(feat.ptr, feat.pitch, feat.N, feat.H, feat.W, feat.C, hp["w1"].data_ptr(), hp["b1"].data_ptr(),
+    if (flags & FLAG_TENSORCORE) and "w1_tc" not in hp:
+        hp["w1_tc"] = tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0])
+    check(lib().deft_heads_forward(feat.ptr, feat.pitch, feat.N, feat.H, feat.W, feat.C, hp["w1"].data_ptr(), _p(hp.get("w1_tc")), hp["b1"].data_ptr(),
                                    hp["head_conv"], hp["w2"].data_ptr(), hp["b2"].data_ptr(), int_array(hp["head_c"]), nh,
                                    ptr_array([o.data_ptr() for o in outs]), flags, ws.data_ptr(), ws.numel(), stream_ptr()),
           "heads_forward")
@@ -202,10 +217,13 @@ def afe_affinity(xp, counts, xn, m, P, pk, out=None, ws=None, flags=0):
         ws = torch.empty(lib().deft_afe_affinity_workspace_bytes(F, P, cemb), dtype=torch.uint8, device=dev)
     if out is None:
         out = torch.zeros((F, P, P + 1), dtype=torch.float32, device=dev)
+    if (flags & FLAG_TENSORCORE) and "tc" not in pk:
+        pk["tc"] = [tc_pack(pk[k], pk[k].shape[1], pk[k].shape[0]) for k in ("w1a", "w1b", "w2", "w3", "w4")]
+    tc = ptr_array([t.data_ptr() for t in pk["tc"]]) if "tc" in pk else None
     check(lib().deft_afe_affinity(xp.data_ptr(), int_array(list(counts)), F, xn.data_ptr(), m, P, cemb, pk["w1a"].data_ptr(),
                                   pk["w1b"].data_ptr(), pk["sh1"].data_ptr(), pk["w2"].data_ptr(), pk["sc2"].data_ptr(),
                                   pk["sh2"].data_ptr(), pk["w3"].data_ptr(), pk["sc3"].data_ptr(), pk["sh3"].data_ptr(),
-                                  pk["w4"].data_ptr(), pk["b4"].data_ptr(), pk["w5"].data_ptr(), C.c_float(pk["b5"]),
+                                  pk["w4"].data_ptr(), pk["b4"].data_ptr(), pk["w5"].data_ptr(), C.c_float(pk["b5"]), tc,
                                   out.data_ptr(), flags, ws.data_ptr(), ws.numel(), stream_ptr()), "afe_affinity")
     return out
 
