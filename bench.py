@@ -125,6 +125,7 @@ def gpu_arm(args, rank, local_rank, world):
     import torch.distributed as dist
     from deft_b200.model.model import create_model
     from deft_b200.opts import Opt
+    from deft_b200.parallel import aggregate_throughput
     from deft_b200.pipeline import FramePipeline
     from deft_b200.synthetic import randomize_
 
@@ -170,10 +171,8 @@ def gpu_arm(args, rank, local_rank, world):
         sampler.stop_flag = True
         sampler.join()
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), sampler.summary()
+        _, ms_max = aggregate_throughput(float(args.steps), ms, device=dev)      # max over ranks of the device time
+        return ms_max, sampler.summary()
 
     # (1) device-resident value: frames already in HBM
     ms_dev, clocks = timed(lambda i: pipe.step_device(frames_dev[i % 4]))
