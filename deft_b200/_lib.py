@@ -19,18 +19,21 @@ _SIGS = {
     "deft_version": (C.c_int, []),
     "deft_last_error": (C.c_char_p, []),
     "deft_device_ok": (C.c_int, []),
-    "deft_tc_tile_n": (C.c_int, [C.c_int, C.c_int]),
+    "deft_launch_count": (C.c_ulonglong, []),
+    "deft_tc_tile_n": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_blob_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_pack_weights": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "deft_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "deft_nchw_to_nhwc": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "deft_nhwc_to_nchw": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
-    "deft_conv2d_bn_act": (C.c_int, [c_ptr_p, c_int_p, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp, c_fp,
-                                     c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, c_fp]),
+    "deft_conv2d_bn_act": (C.c_int, [c_ptr_p, c_int_p, c_int_p, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, C.c_int, c_fp, c_fp,
+                                     c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, c_fp, C.c_size_t,
+                                     c_fp]),
     "deft_stem_conv7x7": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_int, c_fp]),
     "deft_maxpool2x2": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "deft_dcnv2_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "deft_dcnv2_forward": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp,
-                                     c_fp, C.c_int, C.c_int, C.c_uint, c_fp, C.c_size_t, c_fp]),
+    "deft_dcnv2_forward": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int, c_fp, C.c_int, c_fp,
+                                     C.c_int, c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_uint, c_fp, C.c_size_t, c_fp]),
     "deft_upsample_add": (C.c_int, [c_fp, C.c_int, c_fp, c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "deft_heads_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "deft_heads_forward": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int, c_fp, c_fp, c_int_p,
@@ -45,7 +48,7 @@ _SIGS = {
                                    C.c_int, c_fp]),
     "deft_afe_affinity_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "deft_afe_affinity": (C.c_int, [c_fp, c_int_p, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
-                                    c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float, c_ptr_p, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),
+                                    c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float, c_ptr_p, c_int_p, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),
     "deft_lstm_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int,
                                  c_fp, c_fp, c_fp, c_fp]),
 }

@@ -10,9 +10,12 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace deft
 
 extern "C" {
+unsigned long long deft_launch_count(void) { return __atomic_load_n(&deft::g_launches, __ATOMIC_RELAXED); }
 int deft_version(void) { return 100; }
 const char* deft_last_error(void) { return deft::g_err; }
 int deft_device_ok(void) {

@@ -9,6 +9,7 @@
 namespace deft {
 
 void set_error(const char* fmt, ...);
+void count_launch();   // every kernel launch of this library (bench.py's gpu_launches)
 
 inline cudaStream_t to_stream(deft_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -22,6 +23,7 @@ inline cudaStream_t to_stream(deft_stream_t s) { return reinterpret_cast<cudaStr
 
 #define DEFT_CHECK_LAUNCH(name)                                                   \
     do {                                                                          \
+        deft::count_launch();                                                     \
         cudaError_t e__ = cudaGetLastError();                                     \
         if (e__ != cudaSuccess) {                                                 \
             deft::set_error("%s: %s", name, cudaGetErrorString(e__));             \

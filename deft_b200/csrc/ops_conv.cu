@@ -37,50 +37,70 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int src_pitch
 }
 
 // ------------------------------------------------------------------------------------------------
-// 7x7 stem straight from the NCHW image: 16x16 output pixels per block, input halo + weights in smem.
+// 7x7 stem straight from the NCHW image: a block computes 64x16 output pixels, each thread 4 consecutive
+// pixels x 16 channels (the weight LDS.128s are amortised over 4 pixels); input halo + weights in smem.
+constexpr int STEM_TW = 64, STEM_TH = 16, STEM_LD = 72;   // tile row stride (floats), 16 B aligned
 __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ x, int H, int W,
                                                       const float* __restrict__ wp, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, float* __restrict__ out, int out_pitch) {
-    __shared__ float tile[3][22][23];
+    __shared__ __align__(16) float tile[3][STEM_TH + 6][STEM_LD];
     __shared__ __align__(16) float ws[147 * 16];
     const int n = blockIdx.z;
-    const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
+    const int x0 = blockIdx.x * STEM_TW, y0 = blockIdx.y * STEM_TH;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
     for (int i = tid; i < 147 * 16; i += 256) ws[i] = wp[i];
-    for (int i = tid; i < 3 * 22 * 22; i += 256) {
-        int c = i / 484, r = i - c * 484;
-        int ty = r / 22, tx = r - ty * 22;
-        int gy = y0 + ty - 3, gx = x0 + tx - 3;
+    for (int i = tid; i < 3 * (STEM_TH + 6) * (STEM_TW + 6); i += 256) {
+        int c = i / ((STEM_TH + 6) * (STEM_TW + 6)), r = i - c * ((STEM_TH + 6) * (STEM_TW + 6));
+        int yy = r / (STEM_TW + 6), xx = r - yy * (STEM_TW + 6);
+        int gy = y0 + yy - 3, gx = x0 + xx - 3;
         float v = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = x[((size_t)(n * 3 + c) * H + gy) * W + gx];
-        tile[c][ty][tx] = v;
+        tile[c][yy][xx] = v;
     }
     __syncthreads();
-    float acc[16];
+    float acc[4][16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
-    for (int ky = 0; ky < 7; ++ky)
-        for (int kx = 0; kx < 7; ++kx)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float v = tile[c][threadIdx.y + ky][threadIdx.x + kx];
+        for (int o = 0; o < 16; ++o) acc[p][o] = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* row = &tile[c][ty + ky][tx * 4];
+            float v[12];
+            float4 a = *reinterpret_cast<const float4*>(row), b = *reinterpret_cast<const float4*>(row + 4);
+            float2 d = *reinterpret_cast<const float2*>(row + 8);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = d.x; v[9] = d.y;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
                 const float4* w4 = reinterpret_cast<const float4*>(&ws[((ky * 7 + kx) * 3 + c) * 16]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float4 w = w4[q];
-                    acc[q * 4 + 0] += v * w.x; acc[q * 4 + 1] += v * w.y; acc[q * 4 + 2] += v * w.z; acc[q * 4 + 3] += v * w.w;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        acc[p][q * 4 + 0] += v[kx + p] * w.x; acc[p][q * 4 + 1] += v[kx + p] * w.y;
+                        acc[p][q * 4 + 2] += v[kx + p] * w.z; acc[p][q * 4 + 3] += v[kx + p] * w.w;
+                    }
                 }
             }
-    int oy = y0 + threadIdx.y, ox = x0 + threadIdx.x;
-    if (oy < H && ox < W) {
+        }
+    }
+    const int oy = y0 + ty;
+    if (oy >= H) return;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        int ox = x0 + tx * 4 + p;
+        if (ox >= W) break;
         float* o = out + (((size_t)n * H + oy) * W + ox) * out_pitch;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float4 v;
-            v.x = fmaxf(acc[q * 4 + 0] * scale[q * 4 + 0] + shift[q * 4 + 0], 0.f);
-            v.y = fmaxf(acc[q * 4 + 1] * scale[q * 4 + 1] + shift[q * 4 + 1], 0.f);
-            v.z = fmaxf(acc[q * 4 + 2] * scale[q * 4 + 2] + shift[q * 4 + 2], 0.f);
-            v.w = fmaxf(acc[q * 4 + 3] * scale[q * 4 + 3] + shift[q * 4 + 3], 0.f);
+            v.x = fmaxf(acc[p][q * 4 + 0] * scale[q * 4 + 0] + shift[q * 4 + 0], 0.f);
+            v.y = fmaxf(acc[p][q * 4 + 1] * scale[q * 4 + 1] + shift[q * 4 + 1], 0.f);
+            v.z = fmaxf(acc[p][q * 4 + 2] * scale[q * 4 + 2] + shift[q * 4 + 2], 0.f);
+            v.w = fmaxf(acc[p][q * 4 + 3] * scale[q * 4 + 3] + shift[q * 4 + 3], 0.f);
             reinterpret_cast<float4*>(o)[q] = v;
         }
     }
@@ -208,20 +228,19 @@ using namespace deft;
 
 extern "C" {
 
-int deft_tc_tile_n(int ldw, int for_dcn) {
-    int bn = tc_tile_n(ldw);
-    return (for_dcn && bn > 64) ? 64 : bn;
+int deft_tc_tile_n(int ldw, int M, int kind) { return tc_pick_bn(ldw, M, kind); }
+
+size_t deft_tc_blob_bytes(int ldw, int K, int bn) {
+    if (ldw <= 0 || bn <= 0 || ldw % bn != 0 || K <= 0) return 0;
+    return align_up(tc_blob_floats(ldw, K, bn) * sizeof(float), 256);
 }
 
-size_t deft_tc_blob_bytes(int ldw, int K, int for_dcn) {
-    if (ldw <= 0 || ldw % 16 != 0 || K <= 0) return 0;
-    return align_up(tc_blob_floats(ldw, K, deft_tc_tile_n(ldw, for_dcn)) * sizeof(float), 256);
+int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, float* blob, deft_stream_t s) {
+    DEFT_REQUIRE(w_packed && blob && ldw > 0 && bn > 0 && ldw % bn == 0 && K > 0, "tc_pack_weights: bad args");
+    return tc_pack_weights(w_packed, ldw, K, bn, blob, to_stream(s));
 }
 
-int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int for_dcn, float* blob, deft_stream_t s) {
-    DEFT_REQUIRE(w_packed && blob && ldw > 0 && ldw % 16 == 0 && K > 0, "tc_pack_weights: bad args");
-    return tc_pack_weights(w_packed, ldw, K, deft_tc_tile_n(ldw, for_dcn), blob, to_stream(s));
-}
+size_t deft_tc_scratch_bytes(int ldw, int K, int M, int kind) { return tc_splitk_scratch_bytes(ldw, K, M, kind); }
 
 int deft_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int N, int C, int H, int W, deft_stream_t s) {
     DEFT_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && dst_pitch >= C, "nchw_to_nhwc: bad args");
@@ -240,9 +259,9 @@ int deft_nhwc_to_nchw(const float* src, int src_pitch, float* dst, int N, int C,
 }
 
 int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* src_pitch, int nsrc, int N, int H, int W,
-                       const float* w_packed, int ldw, const float* w_tc, const float* scale, const float* shift,
+                       const float* w_packed, int ldw, const float* w_tc, int tc_bn, const float* scale, const float* shift,
                        const float* residual, int res_pitch, float* out, int out_pitch, int Cout, int KH, int KW, int stride, int pad,
-                       unsigned flags, deft_stream_t s) {
+                       unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(srcs && src_c && src_pitch && nsrc >= 1 && nsrc <= DEFT_MAX_SRC, "conv2d: nsrc must be 1..%d", DEFT_MAX_SRC);
     DEFT_REQUIRE(w_packed && out && N > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && stride > 0, "conv2d: bad args");
     ConvAP ap{};
@@ -264,7 +283,7 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
     int M = N * ap.OH * ap.OW;
     int K = KH * KW * ap.Ctot;
     if (flags & DEFT_FLAG_TENSORCORE) {
-        int rc = tc_conv_dispatch(ap, w_tc, ldw, K, M, ep, flags, to_stream(s));
+        int rc = tc_conv_dispatch(ap, w_tc, tc_bn, ldw, K, M, ep, flags, ws, ws_bytes, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;   // EINVAL from the TC engine = shape not covered -> SIMT
     }
     return launch_igemm(ap, w_packed, ldw, K, M, ep, to_stream(s));
@@ -273,7 +292,7 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
 int deft_stem_conv7x7(const float* x, int N, int H, int W, const float* w_packed, const float* scale, const float* shift,
                       float* out, int out_pitch, deft_stream_t s) {
     DEFT_REQUIRE(x && w_packed && scale && shift && out && out_pitch >= 16 && out_pitch % 4 == 0, "stem: bad args");
-    dim3 grid(ceil_div(W, 16), ceil_div(H, 16), N), block(16, 16);
+    dim3 grid(ceil_div(W, STEM_TW), ceil_div(H, STEM_TH), N), block(256);
     stem7x7_kernel<<<grid, block, 0, to_stream(s)>>>(x, H, W, w_packed, scale, shift, out, out_pitch);
     DEFT_CHECK_LAUNCH("stem7x7");
     return DEFT_OK;
@@ -290,14 +309,17 @@ int deft_maxpool2x2(const float* in, int in_pitch, float* out, int out_pitch, in
     return DEFT_OK;
 }
 
+static size_t dcn_om_bytes(int N, int H, int W) { return align_up((size_t)N * H * W * 32 * sizeof(float), 256); }
+
 size_t deft_dcnv2_workspace_bytes(int N, int H, int W, int Cin, int Cout) {
-    (void)Cin; (void)Cout;
-    return align_up((size_t)N * H * W * 32 * sizeof(float), 256);
+    const int M = N * H * W, ldw = (Cout + 15) / 16 * 16;
+    size_t s1 = tc_splitk_scratch_bytes(32, 9 * Cin, M, TC_KIND_CONV), s2 = tc_splitk_scratch_bytes(ldw, 9 * Cin, M, TC_KIND_DCN);
+    return dcn_om_bytes(N, H, W) + (s1 > s2 ? s1 : s2);
 }
 
 int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin, const float* w_om_packed,
-                       const float* b_om, const float* w_om_tc, const float* w_packed, int ldw, const float* w_tc,
-                       const float* scale, const float* shift,
+                       const float* b_om, const float* w_om_tc, int om_bn, const float* w_packed, int ldw, const float* w_tc,
+                       int tc_bn, const float* scale, const float* shift,
                        float* y, int y_pitch, int Cout, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(x && w_om_packed && b_om && w_packed && y && ws, "dcnv2: null argument");
     DEFT_REQUIRE(Cin % 16 == 0 && x_pitch % 4 == 0 && y_pitch % 4 == 0, "dcnv2: Cin%%16 / pitch%%4 (Cin=%d)", Cin);
@@ -307,13 +329,15 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     }
     float* om = reinterpret_cast<float*>(ws);
     const int M = N * H * W;
+    void* scratch = reinterpret_cast<char*>(ws) + dcn_om_bytes(N, H, W);
+    const size_t scratch_bytes = ws_bytes - dcn_om_bytes(N, H, W);
     // 1) offset/mask conv: plain 3x3 conv Cin -> 27 (padded to 32), + bias, no activation
     ConvAP cap{};
     cap.nsrc = 1; cap.Ctot = Cin; cap.src[0] = x; cap.c[0] = Cin; cap.pitch[0] = x_pitch;
     cap.N = N; cap.H = H; cap.W = W; cap.OH = H; cap.OW = W; cap.KH = 3; cap.KW = 3; cap.stride = 1; cap.pad = 1;
     Epilogue e1{nullptr, b_om, nullptr, 0, om, 32, 32, 0};
     int rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w_om_tc, 32, 9 * Cin, M, e1, flags & ~DEFT_FLAG_TF32X1, to_stream(s));
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w_om_tc, om_bn, 32, 9 * Cin, M, e1, flags & ~DEFT_FLAG_TF32X1, scratch, scratch_bytes, to_stream(s));
     if (rc == DEFT_EINVAL) rc = launch_igemm(cap, w_om_packed, 32, 9 * Cin, M, e1, to_stream(s));
     if (rc != DEFT_OK) return rc;
     // 2) deformable gather fused into the GEMM's A producer
@@ -321,7 +345,7 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     dap.x = x; dap.pitch = x_pitch; dap.N = N; dap.H = H; dap.W = W; dap.Cin = Cin; dap.om = om;
     Epilogue e2{scale, shift, nullptr, 0, y, y_pitch, Cout, (flags & DEFT_FLAG_RELU) ? 1 : 0};
     if (flags & DEFT_FLAG_TENSORCORE) {
-        rc = tc_dcn_dispatch(dap, w_tc, ldw, 9 * Cin, M, e2, flags, to_stream(s));
+        rc = tc_dcn_dispatch(dap, w_tc, tc_bn, ldw, 9 * Cin, M, e2, flags, scratch, scratch_bytes, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;
     }
     return launch_igemm(dap, w_packed, ldw, 9 * Cin, M, e2, to_stream(s));
@@ -348,21 +372,9 @@ int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, i
                        float* const* outs, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(feat && w1_packed && b1 && w2 && b2 && head_c && outs && ws, "heads: null argument");
     DEFT_REQUIRE(nheads >= 1 && nheads <= DEFT_MAX_HEADS && head_conv == 256 && Cin % 16 == 0, "heads: nheads<=%d, head_conv==256", DEFT_MAX_HEADS);
-    if (ws_bytes < deft_heads_workspace_bytes(N, H, W, nheads, head_conv)) {
-        set_error("heads: workspace too small");
-        return DEFT_EWORKSPACE;
-    }
     float* hidden = reinterpret_cast<float*>(ws);
     const int HCt = nheads * head_conv;
     const int M = N * H * W;
-    ConvAP cap{};
-    cap.nsrc = 1; cap.Ctot = Cin; cap.src[0] = feat; cap.c[0] = Cin; cap.pitch[0] = feat_pitch;
-    cap.N = N; cap.H = H; cap.W = W; cap.OH = H; cap.OW = W; cap.KH = 3; cap.KW = 3; cap.stride = 1; cap.pad = 1;
-    Epilogue e1{nullptr, b1, nullptr, 0, hidden, HCt, HCt, 1};
-    int rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w1_tc, HCt, 9 * Cin, M, e1, flags, to_stream(s));
-    if (rc == DEFT_EINVAL) rc = launch_igemm(cap, w1_packed, HCt, 9 * Cin, M, e1, to_stream(s));
-    if (rc != DEFT_OK) return rc;
     HeadsOut ho{};
     ho.nheads = nheads;
     int row = 0;
@@ -372,6 +384,24 @@ int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, i
         row += head_c[h];
     }
     ho.total_c = row;
+    ConvAP cap{};
+    cap.nsrc = 1; cap.Ctot = Cin; cap.src[0] = feat; cap.c[0] = Cin; cap.pitch[0] = feat_pitch;
+    cap.N = N; cap.H = H; cap.W = W; cap.OH = H; cap.OW = W; cap.KH = 3; cap.KW = 3; cap.stride = 1; cap.pad = 1;
+    if ((flags & DEFT_FLAG_TENSORCORE) && w1_tc != nullptr) {
+        // fused path: 3x3 conv + bias + ReLU + the head's 1x1 conv in one tcgen05 kernel, no hidden map in HBM
+        HeadsArgs ha{};
+        ha.b1 = b1; ha.w2 = w2; ha.b2 = b2; ha.nheads = nheads; ha.HW = H * W;
+        for (int h = 0; h < nheads; ++h) { ha.out[h] = ho.out[h]; ha.c[h] = ho.c[h]; ha.row0[h] = ho.row0[h]; }
+        int rc = tc_heads_dispatch(cap, w1_tc, 9 * Cin, M, ha, flags, to_stream(s));
+        if (rc != DEFT_EINVAL) return rc;
+    }
+    if (ws_bytes < deft_heads_workspace_bytes(N, H, W, nheads, head_conv)) {   // only the unfused path needs the hidden map
+        set_error("heads: workspace too small");
+        return DEFT_EWORKSPACE;
+    }
+    Epilogue e1{nullptr, b1, nullptr, 0, hidden, HCt, HCt, 1};
+    int rc = launch_igemm(cap, w1_packed, HCt, 9 * Cin, M, e1, to_stream(s));
+    if (rc != DEFT_OK) return rc;
     size_t smem = ((size_t)row * head_conv + (size_t)row * 32) * sizeof(float);
     DEFT_REQUIRE(smem <= 200 * 1024, "heads: too many output channels (%d)", row);
     static size_t attr_smem = 0;

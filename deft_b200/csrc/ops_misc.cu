@@ -22,22 +22,23 @@ __device__ __forceinline__ uint32_t f2u(float f) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// vals = heat * (maxpool3x3(heat) == heat)   (utils.py:69-74)
-__global__ void nms_kernel(const float* __restrict__ hm, float* __restrict__ vals, int H, int W, size_t total) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int p = (int)(i % ((size_t)H * W));
-        int y = p / W, x = p - y * W;
-        const float* pl = hm + (i - p);
-        float h = pl[p], m = h;
+__device__ __forceinline__ float u2f(uint32_t u) {
+    uint32_t b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+    return __uint_as_float(b);
+}
+
+// heat * (maxpool3x3(heat) == heat) for one element (utils.py:69-74)
+__device__ __forceinline__ float nms_value(const float* __restrict__ pl, int p, int H, int W) {
+    int y = p / W, x = p - y * W;
+    float h = pl[p], m = h;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
+    for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                int yy = y + dy, xx = x + dx;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m = fmaxf(m, pl[yy * W + xx]);
-            }
-        vals[i] = (m == h) ? h : 0.0f;
-    }
+        for (int dx = -1; dx <= 1; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) m = fmaxf(m, pl[yy * W + xx]);
+        }
+    return (m == h) ? h : 0.0f;
 }
 
 __device__ void bitonic_sort_desc(unsigned long long* a, int n /* pow2 */) {
@@ -56,83 +57,40 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n /* pow2 */) {
     }
 }
 
-// Per (class, batch) plane: exact top-K by (value desc, index asc).  Radix select for the K-th value,
-// ordered compaction of the winners, bitonic sort.  blockDim = 1024.
-__global__ void __launch_bounds__(1024) topk_class_kernel(const float* __restrict__ vals, int HW, int K,
+// Stage A: every block takes a 4096-element chunk of one (class, batch) plane, applies the 3x3 NMS on the fly and
+// keeps the chunk's top-K by (value desc, index asc).  The global top-K is a subset of the union of chunk top-Ks.
+constexpr int TOPK_CHUNK = 4096;
+__global__ void __launch_bounds__(1024) topk_chunk_kernel(const float* __restrict__ hm, int H, int W, int K, int nchunks,
                                                           unsigned long long* __restrict__ cand) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned int s_prefix, s_kk;
-    __shared__ unsigned int wcnt_gt[32], wcnt_eq[32];
-    __shared__ unsigned int run_gt, run_eq;
-    __shared__ unsigned long long keys[1024];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* v = vals + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * HW;
-    unsigned long long* out = cand + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * K;
-
-    unsigned int prefix = 0, mask = 0, kk = K;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        if (tid < 256) hist[tid] = 0;
-        __syncthreads();
-        for (int i = tid; i < HW; i += 1024) {
-            unsigned int u = f2u(v[i]);
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned int cum = 0;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (cum + hist[b] >= kk) break;
-                cum += hist[b];
-            }
-            s_prefix = prefix | ((unsigned int)b << shift);
-            s_kk = kk - cum;
-        }
-        __syncthreads();
-        prefix = s_prefix;
-        kk = s_kk;
-        mask |= 0xFFu << shift;
-        __syncthreads();
+    __shared__ unsigned long long keys[TOPK_CHUNK];
+    const int HW = H * W;
+    const size_t plane = (size_t)blockIdx.z * gridDim.y + blockIdx.y;
+    const float* pl = hm + plane * HW;
+    for (int e = threadIdx.x; e < TOPK_CHUNK; e += 1024) {
+        int i = blockIdx.x * TOPK_CHUNK + e;
+        unsigned long long key = 0ull;
+        if (i < HW) key = ((unsigned long long)f2u(nms_value(pl, i, H, W)) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
+        keys[e] = key;
     }
-    const unsigned int T = prefix;          // K-th largest value (as ordered uint)
-    const unsigned int n_gt = K - kk;       // strictly greater elements; kk ties to take in index order
-    if (tid == 0) { run_gt = 0; run_eq = 0; }
-    int Kp = 1;
-    while (Kp < K) Kp <<= 1;
-    for (int i = tid; i < Kp; i += 1024) keys[i] = 0ull;
     __syncthreads();
-    for (int base = 0; base < HW; base += 1024) {
-        int i = base + tid;
-        unsigned int u = (i < HW) ? f2u(v[i]) : 0u;
-        bool gt = (i < HW) && (u > T);
-        bool eq = (i < HW) && (u == T);
-        unsigned int bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
-        if (lane == 0) { wcnt_gt[warp] = __popc(bg); wcnt_eq[warp] = __popc(be); }
-        __syncthreads();
-        unsigned int og = run_gt, oe = run_eq;
-        for (int w = 0; w < warp; ++w) { og += wcnt_gt[w]; oe += wcnt_eq[w]; }
-        unsigned int lm = (1u << lane) - 1u;
-        og += __popc(bg & lm);
-        oe += __popc(be & lm);
-        unsigned long long key = ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
-        if (gt) keys[og] = key;
-        if (eq && oe < kk) keys[n_gt + oe] = key;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned int tg = 0, te = 0;
-            for (int w = 0; w < 32; ++w) { tg += wcnt_gt[w]; te += wcnt_eq[w]; }
-            run_gt += tg;
-            run_eq += te;
-        }
-        __syncthreads();
-    }
-    bitonic_sort_desc(keys, Kp);
-    for (int i = tid; i < K; i += 1024) out[i] = keys[i];
+    bitonic_sort_desc(keys, TOPK_CHUNK);
+    unsigned long long* out = cand + (plane * nchunks + blockIdx.x) * K;
+    for (int i = threadIdx.x; i < K; i += 1024) out[i] = keys[i];
+}
+
+// Stage B: per (class, batch) merge of the chunk winners -> the per-class top-K of utils.py:92.
+__global__ void __launch_bounds__(1024) topk_class_merge_kernel(const unsigned long long* __restrict__ cand_chunk, int n, int Np, int K,
+                                                                unsigned long long* __restrict__ cand) {
+    extern __shared__ unsigned long long mkeys[];
+    const size_t plane = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned long long* src = cand_chunk + plane * n;
+    for (int i = threadIdx.x; i < Np; i += 1024) mkeys[i] = (i < n) ? src[i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(mkeys, Np);
+    for (int i = threadIdx.x; i < K; i += 1024) cand[plane * K + i] = mkeys[i];
 }
 
 struct DecodeArgs {
-    const float* vals;
     const unsigned long long* cand;
     const float* reg;
     const float* wh;
@@ -158,7 +116,7 @@ __global__ void __launch_bounds__(1024) decode_merge_kernel(DecodeArgs a, int Np
         unsigned int flatpos = 0xFFFFFFFFu - (unsigned int)(skeys[k] & 0xFFFFFFFFull);
         int cls = (int)(flatpos / (unsigned int)a.K);
         unsigned int idx = 0xFFFFFFFFu - (unsigned int)(cand[flatpos] & 0xFFFFFFFFull);
-        float score = a.vals[((size_t)b * a.C + cls) * HW + idx];
+        float score = u2f((unsigned int)(cand[flatpos] >> 32));
         int yi = (int)(idx / (unsigned int)a.W), xi = (int)(idx - (unsigned int)yi * a.W);
         float ys0 = (float)yi, xs0 = (float)xi;
         size_t o = (size_t)b * a.K + k;
@@ -405,8 +363,11 @@ int deft_sigmoid_output(float* hm, size_t n_hm, float* dep, size_t n_dep, float 
     return DEFT_OK;
 }
 
+static int decode_chunks(int H, int W) { return ceil_div(H * W, TOPK_CHUNK); }
+
 size_t deft_decode_workspace_bytes(int B, int C, int H, int W, int K) {
-    return align_up((size_t)B * C * H * W * sizeof(float), 256) + align_up((size_t)B * C * K * sizeof(unsigned long long), 256);
+    return align_up((size_t)B * C * decode_chunks(H, W) * K * sizeof(unsigned long long), 256) +
+           align_up((size_t)B * C * K * sizeof(unsigned long long), 256);
 }
 
 int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float* reg, const float* wh, const float* ltrb_amodal,
@@ -414,28 +375,33 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
                 void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(hm && scores && inds && clses && ys && xs && ws, "decode: null argument");
     DEFT_REQUIRE(K >= 1 && K <= 1024 && K <= H * W, "decode: K must be in [1, min(1024, H*W)] (K=%d)", K);
-    int Np = 1;
+    const int nchunks = decode_chunks(H, W);
+    int Np = 1, Mp = 1;
     while (Np < C * K) Np <<= 1;
-    DEFT_REQUIRE(Np <= 16384, "decode: C*K too large (%d)", C * K);
+    while (Mp < nchunks * K) Mp <<= 1;
+    DEFT_REQUIRE(Np <= 16384 && Mp <= 16384, "decode: C*K or chunks*K too large (%d, %d)", C * K, nchunks * K);
     if (ws_bytes < deft_decode_workspace_bytes(B, C, H, W, K)) {
         set_error("decode: workspace too small");
         return DEFT_EWORKSPACE;
     }
-    float* vals = reinterpret_cast<float*>(ws);
-    unsigned long long* cand = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + align_up((size_t)B * C * H * W * sizeof(float), 256));
-    size_t total = (size_t)B * C * H * W;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    nms_kernel<<<blocks, 256, 0, to_stream(s)>>>(hm, vals, H, W, total);
-    DEFT_CHECK_LAUNCH("nms");
-    topk_class_kernel<<<dim3(C, B), 1024, 0, to_stream(s)>>>(vals, H * W, K, cand);
-    DEFT_CHECK_LAUNCH("topk_class");
-    DecodeArgs a{vals, cand, reg, wh, ltrb_amodal, scores, (long long*)inds, clses, ys, xs, bboxes, bboxes_amodal, C, H, W, K};
+    unsigned long long* cand_chunk = reinterpret_cast<unsigned long long*>(ws);
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(
+        reinterpret_cast<char*>(ws) + align_up((size_t)B * C * nchunks * K * sizeof(unsigned long long), 256));
+    topk_chunk_kernel<<<dim3(nchunks, C, B), 1024, 0, to_stream(s)>>>(hm, H, W, K, nchunks, cand_chunk);
+    DEFT_CHECK_LAUNCH("topk_chunk");
+    static size_t attr_b = 48 * 1024, attr_c = 48 * 1024;
+    size_t smem_b = (size_t)Mp * sizeof(unsigned long long);
+    if (smem_b > attr_b) {
+        cudaFuncSetAttribute(topk_class_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+        attr_b = smem_b;
+    }
+    topk_class_merge_kernel<<<dim3(C, B), 1024, smem_b, to_stream(s)>>>(cand_chunk, nchunks * K, Mp, K, cand);
+    DEFT_CHECK_LAUNCH("topk_class_merge");
+    DecodeArgs a{cand, reg, wh, ltrb_amodal, scores, (long long*)inds, clses, ys, xs, bboxes, bboxes_amodal, C, H, W, K};
     size_t smem = (size_t)Np * sizeof(unsigned long long);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
+    if (smem > attr_c) {
         cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
+        attr_c = smem;
     }
     decode_merge_kernel<<<B, 1024, smem, to_stream(s)>>>(a, Np);
     DEFT_CHECK_LAUNCH("decode_merge");
@@ -495,14 +461,14 @@ size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb) {
     return t;
 }
 
-static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, const float* Wtc, int ldw, const float* sc, const float* sh,
+static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, const float* Wtc, int tcbn, int ldw, const float* sc, const float* sh,
                       float* out, int ldo, int Cout, int relu, unsigned flags, cudaStream_t st) {
     ConvAP ap{};
     ap.nsrc = 1; ap.Ctot = K; ap.src[0] = A; ap.c[0] = K; ap.pitch[0] = lda;
     ap.N = 1; ap.H = 1; ap.W = Mrows; ap.OH = 1; ap.OW = Mrows; ap.KH = 1; ap.KW = 1; ap.stride = 1; ap.pad = 0;
     Epilogue ep{sc, sh, nullptr, 0, out, ldo, Cout, relu};
     if (flags & DEFT_FLAG_TENSORCORE) {
-        int rc = tc_conv_dispatch(ap, Wtc, ldw, K, Mrows, ep, flags, st);
+        int rc = tc_conv_dispatch(ap, Wtc, tcbn, ldw, K, Mrows, ep, flags, nullptr, 0, st);
         if (rc != DEFT_EINVAL) return rc;
     }
     return launch_igemm(ap, Wp, ldw, K, Mrows, ep, st);
@@ -511,7 +477,7 @@ static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp
 int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb, const float* w1a,
                       const float* w1b, const float* sh1, const float* w2, const float* sc2, const float* sh2, const float* w3,
                       const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5,
-                      const float* const* tc, float* out,
+                      const float* const* tc, const int* tcbn, float* out,
                       unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
     DEFT_REQUIRE(xp && n_host && xn && out && ws && w1a && w1b && sh1 && w2 && w3 && w4 && w5, "afe_affinity: null argument");
     DEFT_REQUIRE(F >= 1 && F <= AFF_MAX_FRAMES && m >= 1 && m <= P && P <= 1024 && Cemb % 16 == 0,
@@ -537,17 +503,19 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
     // layer 1, decomposed: Au' = bnfold(W1a u_i + b1), Bv' = bnfold-scale(W1b v_j)
     const float* t1a = tc ? tc[0] : nullptr; const float* t1b = tc ? tc[1] : nullptr; const float* t2 = tc ? tc[2] : nullptr;
     const float* t3 = tc ? tc[3] : nullptr; const float* t4 = tc ? tc[4] : nullptr;
-    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, t1a, 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, t1b, 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    int bn[5] = {0, 0, 0, 0, 0};
+    if (tc && tcbn) for (int i = 0; i < 5; ++i) bn[i] = tcbn[i];
+    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, t1a, bn[0], 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, t1b, bn[1], 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
     // layer 2 with the pair expansion relu(Au'_i + Bv'_j) as the A producer
     pap.au = au; pap.bv = bv; pap.P = P; pap.m = m; pap.F = F; pap.ld = 512;
     Epilogue e2{sc2, sh2, nullptr, 0, h2, 256, 256, 1};
     rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_pair_dispatch(pap, t2, 256, 512, M, e2, flags, st);
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_pair_dispatch(pap, t2, bn[2], 256, 512, M, e2, flags, st);
     if (rc == DEFT_EINVAL) rc = launch_igemm(pap, w2, 256, 512, M, e2, st);
     if (rc != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h2, 256, M, 256, w3, t3, 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h3, 128, M, 128, w4, t4, 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h2, 256, M, 256, w3, t3, bn[3], 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(h3, 128, M, 128, w4, t4, bn[4], 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
     affinity_final_kernel<<<ceil_div(M, 32), 256, 0, st>>>(h4, w5, b5, S, M);
     DEFT_CHECK_LAUNCH("affinity_final");
     sa.m = m; sa.P = P;

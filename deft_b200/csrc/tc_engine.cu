@@ -2,16 +2,19 @@
 //
 //   D[128 px, BN couts] (fp32, TMEM)  +=  A[128 x 32] (smem, K-major, SWIZZLE_128B)  x  B[BN x 32] (smem, K-major)
 //
-// * A is never materialised in HBM: 8 producer warps build each 128x32 tile on the fly (im2col over
-//   NHWC sources, or the DCNv2 bilinear gather) and write it straight into the UMMA canonical layout.
-// * B (weights) is pre-packed by tc_pack_weights_kernel as ready-made swizzled smem tile images, so one
-//   elected thread streams it in with cp.async.bulk (TMA bulk copy, mbarrier complete_tx).
-// * fp32 parity: 3xTF32 error compensation -- every operand is split x = hi + lo (hi = rna_tf32(x)),
-//   D += hi*hi + lo*hi + hi*lo, three kind::tf32 MMAs per k-step into the same TMEM accumulator
-//   (the dropped lo*lo term is O(2^-22)).  DEFT_FLAG_TF32X1 issues only hi*hi.
-// * Warp roles: warps 0-7 A producers then epilogue (tcgen05.ld -> scale/shift/residual/ReLU -> NHWC),
-//   warp 8 lane 0 MMA issuer, warp 9 TMEM allocator + lane 0 weight-tile bulk copies.
-// * mbarrier ring of S stages: full_a (256 producer arrivals), full_b (tx bytes), empty (tcgen05.commit).
+// * A is never materialised in HBM: 8 producer warps build each 128x32 tile on the fly (im2col over NHWC
+//   sources, the DCNv2 bilinear gather, or the affinity pair expansion) and write it straight into the UMMA
+//   canonical layout.  Global loads are software-pipelined in registers (issue for k-block kb+D while kb is
+//   converted/stored), so the mainloop runs at the tensor pipe's pace, not at L2 latency.
+// * B (weights) is pre-packed by tc_pack_weights_kernel as ready-made swizzled smem tile images, streamed in
+//   by one elected thread with cp.async.bulk (TMA bulk copy, mbarrier complete_tx).
+// * fp32 parity: 3xTF32 error compensation -- x = hi + lo (hi = rna_tf32(x)), D += hi*hi + lo*hi + hi*lo, three
+//   kind::tf32 MMAs per k-step into the same TMEM accumulator.  DEFT_FLAG_TF32X1 issues only hi*hi.
+// * Small-M layers (DLA levels 4/5 at 1/16, 1/32 resolution) are split along K over blockIdx.z; partials go
+//   to caller scratch and a deterministic reduce kernel applies the epilogue (no atomics).
+// * Warp roles: warps 0-7 A producers then epilogue (tcgen05.ld -> epilogue functor), warp 8 lane 0 MMA
+//   issuer, warp 9 TMEM allocator + lane 0 weight-tile bulk copies.  mbarrier ring of S stages:
+//   full_a (256 producer arrivals), full_b (tx bytes), empty (tcgen05.commit).
 #include "tc_engine.cuh"
 
 namespace deft {
@@ -22,6 +25,7 @@ constexpr int TC_PRODUCERS = 256;
 constexpr int TC_THREADS = 320;                 // 8 producer/epilogue warps + MMA warp + TMEM/B warp
 constexpr int TC_A_TILE = TC_BM * 128;          // bytes
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int TC_NUM_SMS = 148;
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -50,7 +54,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {
-            printf("deft tc_engine: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+            printf("deft tc_engine: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x, bar, parity);
             __trap();
         }
     }
@@ -118,10 +123,14 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(
 
 // ------------------------------------------------------------------------------------------------ A producers
 // Thread t (0..255) owns 16-byte chunk c = t & 7 of rows r_i = (t >> 3) + 32 i, i = 0..3, of every k-block.
+// issue(kb, raw): start the global loads of k-block kb into registers; combine(kb, raw, v): turn them into
+// the 4 A-tile chunks.  DEPTH = how many k-blocks of loads are kept in flight.
 struct TcConvAP {
     ConvAP a;
     int K;
     static constexpr int kExtraSmemBytes = 0;
+    static constexpr int RAW = 4;
+    static constexpr int DEPTH = 2;
     int n_[4], oy_[4], ox_[4];
     unsigned valid_;
     __device__ __forceinline__ void init(int m0, int M, unsigned char*) {
@@ -134,11 +143,11 @@ struct TcConvAP {
             int q = v ? p : 0;
             n_[i] = q / (a.OH * a.OW);
             int r = q - n_[i] * (a.OH * a.OW);
-            oy_[i] = r / a.OW;
-            ox_[i] = r - oy_[i] * a.OW;
+            oy_[i] = (r / a.OW) * a.stride - a.pad;
+            ox_[i] = (r - (r / a.OW) * a.OW) * a.stride - a.pad;
         }
     }
-    __device__ __forceinline__ void load4(int kb, float4 (&v)[4]) const {
+    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
         int k = kb * TC_BK + (threadIdx.x & 7) * 4;
         int tap = k / a.Ctot;
         int cc = k - tap * a.Ctot;
@@ -150,12 +159,16 @@ struct TcConvAP {
         const bool kok = k < K;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int iy = oy_[i] * a.stride - a.pad + ky;
-            int ix = ox_[i] * a.stride - a.pad + kx;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int iy = oy_[i] + ky;
+            int ix = ox_[i] + kx;
+            raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kok && ((valid_ >> i) & 1u) && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-                v[i] = ldg4(base + (((size_t)n_[i] * a.H + iy) * a.W + ix) * pitch + cc);
+                raw[i] = ldg4(base + (((size_t)n_[i] * a.H + iy) * a.W + ix) * pitch + cc);
         }
+    }
+    __device__ __forceinline__ void combine(int, const float4 (&raw)[RAW], float4 (&v)[4]) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = raw[i];
     }
 };
 
@@ -163,6 +176,8 @@ struct TcDcnAP {
     DcnAP a;
     int K;
     static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
+    static constexpr int RAW = 16;
+    static constexpr int DEPTH = 1;
     int4* tabO_;
     float4* tabW_;
     __device__ __forceinline__ void init(int m0, int M, unsigned char* extra) {
@@ -196,28 +211,37 @@ struct TcDcnAP {
                     if (y1ok && x1ok) { o.w = base + (y0 + 1) * W + x0 + 1; w.w = ly * lx * mk; }
                 }
             }
-            tabO_[idx] = o;
+            tabO_[idx] = o;       // corners with zero weight point at pixel 0: always a valid address
             tabW_[idx] = w;
         }
         // producers-only barrier (named barrier 1, 256 threads): the table is private to them
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    __device__ __forceinline__ void load4(int kb, float4 (&v)[4]) const {
-        int k = kb * TC_BK + (threadIdx.x & 7) * 4;
-        int tap = k / a.Cin;
-        int cc = k - tap * a.Cin;
-        const float* x = a.x;
+    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
+        const int kbpt = a.Cin / TC_BK;                 // k-blocks per tap (Cin % 32 == 0)
+        const int tap = kb / kbpt;
+        const int cc = (kb - tap * kbpt) * TC_BK + (threadIdx.x & 7) * 4;
+        const float* x = a.x + cc;
         const int pitch = a.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int row = (threadIdx.x >> 3) + 32 * i;
-            int4 o = tabO_[row * 9 + tap];
-            float4 w = tabW_[row * 9 + tap];
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (w.x != 0.f) { float4 t = ldg4(x + (size_t)o.x * pitch + cc); acc.x += w.x * t.x; acc.y += w.x * t.y; acc.z += w.x * t.z; acc.w += w.x * t.w; }
-            if (w.y != 0.f) { float4 t = ldg4(x + (size_t)o.y * pitch + cc); acc.x += w.y * t.x; acc.y += w.y * t.y; acc.z += w.y * t.z; acc.w += w.y * t.w; }
-            if (w.z != 0.f) { float4 t = ldg4(x + (size_t)o.z * pitch + cc); acc.x += w.z * t.x; acc.y += w.z * t.y; acc.z += w.z * t.z; acc.w += w.z * t.w; }
-            if (w.w != 0.f) { float4 t = ldg4(x + (size_t)o.w * pitch + cc); acc.x += w.w * t.x; acc.y += w.w * t.y; acc.z += w.w * t.z; acc.w += w.w * t.w; }
+            const int4 o = tabO_[((threadIdx.x >> 3) + 32 * i) * 9 + tap];
+            raw[i * 4 + 0] = ldg4(x + (size_t)o.x * pitch);
+            raw[i * 4 + 1] = ldg4(x + (size_t)o.y * pitch);
+            raw[i * 4 + 2] = ldg4(x + (size_t)o.z * pitch);
+            raw[i * 4 + 3] = ldg4(x + (size_t)o.w * pitch);
+        }
+    }
+    __device__ __forceinline__ void combine(int kb, const float4 (&raw)[RAW], float4 (&v)[4]) const {
+        const int tap = kb / (a.Cin / TC_BK);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 w = tabW_[((threadIdx.x >> 3) + 32 * i) * 9 + tap];
+            float4 acc;
+            acc.x = w.x * raw[i * 4].x; acc.y = w.x * raw[i * 4].y; acc.z = w.x * raw[i * 4].z; acc.w = w.x * raw[i * 4].w;
+            acc.x += w.y * raw[i * 4 + 1].x; acc.y += w.y * raw[i * 4 + 1].y; acc.z += w.y * raw[i * 4 + 1].z; acc.w += w.y * raw[i * 4 + 1].w;
+            acc.x += w.z * raw[i * 4 + 2].x; acc.y += w.z * raw[i * 4 + 2].y; acc.z += w.z * raw[i * 4 + 2].z; acc.w += w.z * raw[i * 4 + 2].w;
+            acc.x += w.w * raw[i * 4 + 3].x; acc.y += w.w * raw[i * 4 + 3].y; acc.z += w.w * raw[i * 4 + 3].z; acc.w += w.w * raw[i * 4 + 3].w;
             v[i] = acc;
         }
     }
@@ -228,6 +252,8 @@ struct TcPairAP {
     PairAP a;
     int K;
     static constexpr int kExtraSmemBytes = 0;
+    static constexpr int RAW = 8;
+    static constexpr int DEPTH = 2;
     const float* pa_[4];
     const float* pb_[4];
     __device__ __forceinline__ void init(int m0, int M, unsigned char*) {
@@ -246,45 +272,171 @@ struct TcPairAP {
             }
         }
     }
-    __device__ __forceinline__ void load4(int kb, float4 (&v)[4]) const {
+    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
         const int k = kb * TC_BK + (threadIdx.x & 7) * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (pa_[i] != nullptr && k < K) {
-                float4 x = ldg4(pa_[i] + k), y = ldg4(pb_[i] + k);
-                v[i].x = fmaxf(x.x + y.x, 0.f); v[i].y = fmaxf(x.y + y.y, 0.f);
-                v[i].z = fmaxf(x.z + y.z, 0.f); v[i].w = fmaxf(x.w + y.w, 0.f);
+                raw[2 * i] = ldg4(pa_[i] + k);
+                raw[2 * i + 1] = ldg4(pb_[i] + k);
+            }
+        }
+    }
+    __device__ __forceinline__ void combine(int, const float4 (&raw)[RAW], float4 (&v)[4]) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i].x = fmaxf(raw[2 * i].x + raw[2 * i + 1].x, 0.f); v[i].y = fmaxf(raw[2 * i].y + raw[2 * i + 1].y, 0.f);
+            v[i].z = fmaxf(raw[2 * i].z + raw[2 * i + 1].z, 0.f); v[i].w = fmaxf(raw[2 * i].w + raw[2 * i + 1].w, 0.f);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// Interface: kSmemBytes; setup(smem, tid) by the 256 producer threads before the mainloop;
+// run<BN>(tmem_base, smem, warp, lane, m0, M, ntile) by warps 0-7 once the accumulator is complete.
+struct EpiStd {
+    Epilogue e;
+    float* partial;      // split-K scratch [splits][M][ldp] or nullptr
+    int ldp;
+    static constexpr int kSmemBytes = 0;
+    __device__ __forceinline__ void setup(unsigned char*, int) const {}
+    template <int BN>
+    __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char*, int warp, int lane, int m0, int M, int ntile) const {
+        const int lane_base = (warp & 3) * 32;
+        const int p = m0 + lane_base + lane;
+        constexpr int COLS_PER_HALF = BN / 2;     // warps 0-3: first half of the columns, warps 4-7: second half
+        const int col0 = (warp >> 2) * COLS_PER_HALF;
+#pragma unroll 1
+        for (int c = 0; c < COLS_PER_HALF; c += 8) {
+            float v[8];
+            tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + c), v);
+            const int co = ntile * BN + col0 + c;
+            if (p >= M) continue;
+            if (partial != nullptr) {
+                float* dst = partial + ((size_t)blockIdx.z * M + p) * ldp + co;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int cq = co + q * 4;
+                if (cq >= e.Cout) break;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.scale) sc = ldg4(e.scale + cq);
+                if (e.shift) sh = ldg4(e.shift + cq);
+                float4 o;
+                o.x = v[q * 4 + 0] * sc.x + sh.x; o.y = v[q * 4 + 1] * sc.y + sh.y;
+                o.z = v[q * 4 + 2] * sc.z + sh.z; o.w = v[q * 4 + 3] * sc.w + sh.w;
+                if (e.residual) {
+                    float4 rr = ldg4(e.residual + (size_t)p * e.res_pitch + cq);
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(e.out + (size_t)p * e.out_pitch + cq) = o;
             }
         }
     }
 };
 
+// CenterNet heads, fused: N tile = one head's 256 hidden channels.  hidden = relu(acc + b1) never leaves the SM;
+// the head's 1x1 conv (256 -> C_h <= 16) is a per-row dot product against w2 staged in smem; planar NCHW store.
+constexpr int HEADS_MAXC = 16;
+struct EpiHeads {
+    const float* b1;     // [nheads*256]
+    const float* w2;     // [sum C_h][256]
+    const float* b2;     // [sum C_h]
+    float* out[DEFT_MAX_HEADS];
+    int c[DEFT_MAX_HEADS];
+    int row0[DEFT_MAX_HEADS];
+    int HW;
+    static constexpr int kSmemBytes = HEADS_MAXC * 256 * 4 + 256 * 4 + HEADS_MAXC * TC_BM * 4;
+    __device__ __forceinline__ void setup(unsigned char* smem, int tid) const {
+        float* w2s = reinterpret_cast<float*>(smem);
+        float* b1s = w2s + HEADS_MAXC * 256;
+        const int h = blockIdx.y;
+        const int ch = c[h];
+        for (int i = tid; i < ch * 256; i += TC_PRODUCERS) w2s[i] = w2[(size_t)row0[h] * 256 + i];
+        b1s[tid] = b1[h * 256 + tid];
+        // visibility to all epilogue warps is guaranteed by the producers' later named barrier in run()
+    }
+    template <int BN>
+    __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char* smem, int warp, int lane, int m0, int M, int ntile) const {
+        static_assert(BN == 256, "EpiHeads needs one 256-wide tile per head");
+        const float* w2s = reinterpret_cast<const float*>(smem);
+        const float* b1s = w2s + HEADS_MAXC * 256;
+        float* part = const_cast<float*>(b1s) + 256;          // [HEADS_MAXC][128] partials of the upper column half
+        const int h = ntile;
+        const int ch = c[h];
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int p = m0 + row;
+        const int col0 = (warp >> 2) * 128;
+        float acc[HEADS_MAXC];
+#pragma unroll
+        for (int j = 0; j < HEADS_MAXC; ++j) acc[j] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // w2s / b1s written by setup() are visible
+#pragma unroll 1
+        for (int cb = 0; cb < 128; cb += 8) {
+            float v[8];
+            tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + cb), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + b1s[col0 + cb + j], 0.f);
+#pragma unroll
+            for (int o = 0; o < HEADS_MAXC; ++o) {
+                if (o < ch) {
+                    const float4 wa = *reinterpret_cast<const float4*>(w2s + o * 256 + col0 + cb);
+                    const float4 wb = *reinterpret_cast<const float4*>(w2s + o * 256 + col0 + cb + 4);
+                    acc[o] += v[0] * wa.x + v[1] * wa.y + v[2] * wa.z + v[3] * wa.w + v[4] * wb.x + v[5] * wb.y + v[6] * wb.z + v[7] * wb.w;
+                }
+            }
+        }
+        if (warp >= 4) {
+#pragma unroll
+            for (int o = 0; o < HEADS_MAXC; ++o)
+                if (o < ch) part[o * TC_BM + row] = acc[o];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp < 4 && p < M) {
+            const int n = p / HW, q = p - n * HW;
+#pragma unroll
+            for (int o = 0; o < HEADS_MAXC; ++o)
+                if (o < ch) out[h][((size_t)n * ch + o) * HW + q] = acc[o] + part[o * TC_BM + row] + b2[row0[h] + o];
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ kernel
-template <class AP, int BN, int NPASS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, int nkb, int M, int stages,
-                                                                 Epilogue ep) {
+template <class AP, int BN, int NPASS, class EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, int nkb_total, int kb_per_split,
+                                                                 int M, int stages, EPI epi) {
     constexpr int B_TILE = BN * 128;                      // bytes of one B part (hi or lo)
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms must sit on 1024 B boundaries)
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     unsigned char* smem = smem_raw + pad;
-    const uint32_t sbase = raw + pad;
-    // layout: [stages x STAGE_BYTES] [barriers 64 B-aligned] [tmem slot] [AP extra]
+    const uint32_t sbase = raw_addr + pad;
+    // layout: [stages x STAGE_BYTES] [barriers + tmem slot: 256 B] [AP extra] [EPI extra]
     const uint32_t bar_base = sbase + (uint32_t)stages * STAGE_BYTES;
     auto full_a = [&](int s) { return bar_base + 8u * s; };
     auto full_b = [&](int s) { return bar_base + 8u * (8 + s); };
     auto empty = [&](int s) { return bar_base + 8u * (16 + s); };
     const uint32_t accum_bar = bar_base + 8u * 24;
     const uint32_t tmem_slot = bar_base + 8u * 25;
-    unsigned char* extra = smem + (size_t)stages * STAGE_BYTES + 256;
+    unsigned char* ap_extra = smem + (size_t)stages * STAGE_BYTES + 256;
+    unsigned char* epi_extra = ap_extra + AP::kExtraSmemBytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * TC_BM;
     const int ntile = blockIdx.y;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int kb1 = min(nkb_total, kb0 + kb_per_split);
+    const int nkb = kb1 - kb0;                            // >= 1 by construction of the split
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -304,72 +456,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
 
     if (warp < 8) {
         // ===================== A producers =====================
-        ap.init(m0, M, extra);
+        ap.init(m0, M, ap_extra);
+        epi.setup(epi_extra, tid);
         const int chunk = tid & 7;
         const int row0 = tid >> 3;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % stages;
-            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-            float4 v[4];
-            ap.load4(kb, v);                      // global loads first, then wait for the slot
-            mbar_wait(empty(s), ph ^ 1u);
-            unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
-            unsigned char* a_lo = a_hi + TC_A_TILE;
+        float4 raw[AP::DEPTH][AP::RAW];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t off = swz(row0 + 32 * i, chunk);
-                float4 h;
-                h.x = tf32_rna(v[i].x); h.y = tf32_rna(v[i].y); h.z = tf32_rna(v[i].z); h.w = tf32_rna(v[i].w);
-                *reinterpret_cast<float4*>(a_hi + off) = h;
-                if (NPASS == 3) {
-                    float4 l;
-                    l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
-                    *reinterpret_cast<float4*>(a_lo + off) = l;
+        for (int d = 0; d < AP::DEPTH; ++d)
+            if (d < nkb) ap.issue(kb0 + d, raw[d]);
+        for (int it = 0; it < nkb; it += AP::DEPTH) {
+#pragma unroll
+            for (int d = 0; d < AP::DEPTH; ++d) {
+                const int i = it + d;                     // local k-block index
+                if (i < nkb) {
+                    float4 v[4];
+                    ap.combine(kb0 + i, raw[d], v);
+                    if (i + AP::DEPTH < nkb) ap.issue(kb0 + i + AP::DEPTH, raw[d]);
+                    const int s = i % stages;
+                    const uint32_t ph = (uint32_t)(i / stages) & 1u;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
+                    unsigned char* a_lo = a_hi + TC_A_TILE;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint32_t off = swz(row0 + 32 * r, chunk);
+                        float4 h;
+                        h.x = tf32_rna(v[r].x); h.y = tf32_rna(v[r].y); h.z = tf32_rna(v[r].z); h.w = tf32_rna(v[r].w);
+                        *reinterpret_cast<float4*>(a_hi + off) = h;
+                        if (NPASS == 3) {
+                            float4 l;
+                            l.x = v[r].x - h.x; l.y = v[r].y - h.y; l.z = v[r].z - h.z; l.w = v[r].w - h.w;
+                            *reinterpret_cast<float4*>(a_lo + off) = l;
+                        }
+                    }
+                    fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                    mbar_arrive(full_a(s));
                 }
             }
-            fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core (async proxy)
-            mbar_arrive(full_a(s));
         }
         // ===================== epilogue =====================
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int lane_base = (warp & 3) * 32;
-        const int p = m0 + lane_base + lane;
-        constexpr int COLS_PER_HALF = BN / 2;     // warps 0-3: first half of the columns, warps 4-7: second half
-        const int col0 = (warp >> 2) * COLS_PER_HALF;
-#pragma unroll 1
-        for (int c = 0; c < COLS_PER_HALF; c += 8) {
-            float v[8];
-            tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + c), v);
-            const int co = ntile * BN + col0 + c;
-            if (p < M && co < ep.Cout) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int cq = co + q * 4;
-                    if (cq >= ep.Cout) break;
-                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ep.scale) sc = ldg4(ep.scale + cq);
-                    if (ep.shift) sh = ldg4(ep.shift + cq);
-                    float4 o;
-                    o.x = v[q * 4 + 0] * sc.x + sh.x; o.y = v[q * 4 + 1] * sc.y + sh.y;
-                    o.z = v[q * 4 + 2] * sc.z + sh.z; o.w = v[q * 4 + 3] * sc.w + sh.w;
-                    if (ep.residual) {
-                        float4 rr = ldg4(ep.residual + (size_t)p * ep.res_pitch + cq);
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
-                    if (ep.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    *reinterpret_cast<float4*>(ep.out + (size_t)p * ep.out_pitch + cq) = o;
-                }
-            }
-        }
+        epi.template run<BN>(tmem_base, epi_extra, warp, lane, m0, M, ntile);
         tc_fence_before();
     } else if (warp == 8) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % stages;
+                const uint32_t ph = (uint32_t)(i / stages) & 1u;
                 mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
@@ -380,11 +516,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
-                    umma_tf32(tmem_base, da_hi, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     if (NPASS == 3) {
+                        // small terms first, so the big hi*hi product is added to an already-formed correction
                         const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
-                        umma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+                        umma_tf32(tmem_base, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
                         umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+                        umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, da_hi, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(empty(s));            // slot free once these MMAs have read it
@@ -396,14 +535,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
         // ===================== weight-tile bulk copies (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * nkb) * (2 * B_TILE);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * nkb_total + kb0) * (2 * B_TILE);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % stages;
+                const uint32_t ph = (uint32_t)(i / stages) & 1u;
                 mbar_wait(empty(s), ph ^ 1u);
                 const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
                 mbar_arrive_expect_tx(full_b(s), bytes);
-                bulk_g2s(dst, src + (size_t)kb * (2 * B_TILE), bytes, full_b(s));
+                bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
             }
         }
         __syncwarp();
@@ -412,6 +551,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     if (warp == 9) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// Deterministic split-K tail: out = epilogue(sum_z partial[z]).
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int ldp, Epilogue e) {
+    const int c4 = e.Cout / 4;
+    size_t total = (size_t)M * c4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int p = (int)(i / c4), co = (int)(i - (size_t)p * c4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < splits; ++z) {
+            float4 t = ldg4(partial + ((size_t)z * M + p) * ldp + co);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.scale) sc = ldg4(e.scale + co);
+        if (e.shift) sh = ldg4(e.shift + co);
+        float4 o;
+        o.x = acc.x * sc.x + sh.x; o.y = acc.y * sc.y + sh.y; o.z = acc.z * sc.z + sh.z; o.w = acc.w * sc.w + sh.w;
+        if (e.residual) {
+            float4 rr = ldg4(e.residual + (size_t)p * e.res_pitch + co);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(e.out + (size_t)p * e.out_pitch + co) = o;
     }
 }
 
@@ -437,49 +601,82 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, in
 }
 
 // ------------------------------------------------------------------------------------------------ host
-int tc_tile_n(int ldw) {
-    if (ldw % 128 == 0) return 128;
-    if (ldw % 64 == 0) return 64;
-    if (ldw % 32 == 0) return 32;
-    return 16;
+// Tile-N choice.  Depends only on (ldw, M, kind) so the packer and the dispatcher always agree; the chosen
+// value also travels explicitly with every call (tc_bn).
+int tc_pick_bn(int ldw, int M, int kind) {
+    if (kind == TC_KIND_HEADS) return 256;
+    const int max_bn = (kind == TC_KIND_DCN) ? 64 : 128;
+    const int mt = ceil_div(M, TC_BM);
+    int best = 0;
+    for (int bn = max_bn; bn >= 32; bn >>= 1) {
+        if (ldw % bn != 0) continue;
+        if (best == 0) best = bn;                        // largest dividing tile
+        if (mt * (ldw / bn) >= 120) return bn;           // enough CTAs for one wave
+        if (bn == 64) break;                             // below 64 the redundant A gathers cost more than split-K
+    }
+    if (best == 0) best = (ldw % 32 == 0) ? 32 : 16;
+    return best;                                         // too few CTAs either way: keep the widest tile, split K instead
+}
+static int tc_pick_splits(int ctas, int nkb) {
+    if (ctas >= 100) return 1;
+    int s = TC_NUM_SMS / ctas;
+    int max_s = nkb / 6;                                 // keep >= 6 k-blocks per split
+    if (s > max_s) s = max_s;
+    if (s > 16) s = 16;
+    return s < 1 ? 1 : s;
 }
 size_t tc_blob_floats(int ldw, int K, int bn) {
     int nkb = ceil_div(K, TC_BK);
     return (size_t)(ldw / bn) * nkb * 2 * bn * TC_BK;
 }
+size_t tc_splitk_scratch_bytes(int ldw, int K, int M, int kind) {
+    const int bn = tc_pick_bn(ldw, M, kind);
+    const int splits = tc_pick_splits(ceil_div(M, TC_BM) * (ldw / bn), ceil_div(K, TC_BK));
+    return splits > 1 ? align_up((size_t)splits * M * ldw * sizeof(float), 256) : 0;
+}
 
-template <class AP, int BN, int NPASS>
-static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, const Epilogue& ep, cudaStream_t st) {
+template <class AP, int BN, int NPASS, class EPI>
+static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int splits, EPI epi, cudaStream_t st) {
     constexpr int B_TILE = BN * 128;
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
-    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + AP::kExtraSmemBytes;
+    const int fixed = 1024 /*align*/ + 256 /*barriers*/ + AP::kExtraSmemBytes + EPI::kSmemBytes;
+    const int kb_per_split = ceil_div(nkb, splits);
+    splits = ceil_div(nkb, kb_per_split);                // no empty split
     int stages = (TC_SMEM_LIMIT - fixed) / STAGE_BYTES;
     if (stages > 4) stages = 4;
-    if (stages > nkb) stages = nkb < 1 ? 1 : nkb;
-    if (stages < 2 && nkb > 1) return DEFT_EINVAL;
+    if (stages > kb_per_split) stages = kb_per_split;
+    if (stages < 1 || (stages < 2 && kb_per_split > 1)) return DEFT_EINVAL;
     size_t smem = (size_t)stages * STAGE_BYTES + fixed;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(tc_igemm_kernel<AP, BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
+        if (cudaFuncSetAttribute(tc_igemm_kernel<AP, BN, NPASS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
             set_error("tc_engine: cannot raise dynamic smem limit");
             return DEFT_ECUDA;
         }
         attr_done = true;
     }
-    dim3 grid(ceil_div(M, TC_BM), n_tiles);
-    tc_igemm_kernel<AP, BN, NPASS><<<grid, TC_THREADS, smem, st>>>(ap, blob, nkb, M, stages, ep);
+    dim3 grid(ceil_div(M, TC_BM), n_tiles, splits);
+    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, nkb, kb_per_split, M, stages, epi);
     DEFT_CHECK_LAUNCH("tc_igemm_kernel");
     return DEFT_OK;
 }
 
 template <class AP>
-static int tc_dispatch(AP ap, const float* blob, int ldw, int K, int M, const Epilogue& ep, unsigned flags, int bn, cudaStream_t st) {
-    if (blob == nullptr || ldw % bn != 0 || ep.Cout % 4 != 0) return DEFT_EINVAL;
+static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                       size_t scratch_bytes, cudaStream_t st) {
+    if (blob == nullptr || bn <= 0 || ldw % bn != 0 || ep.Cout % 4 != 0) return DEFT_EINVAL;
     const int nkb = ceil_div(K, TC_BK), nt = ldw / bn;
+    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
+    if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
+    if (splits > 1) splits = ceil_div(nkb, ceil_div(nkb, splits));
+    EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
     const bool x1 = (flags & DEFT_FLAG_TF32X1) != 0;
-#define TC_CASE(BNV)                                                                                   \
-    case BNV:                                                                                          \
-        return x1 ? tc_launch<AP, BNV, 1>(ap, blob, nkb, M, nt, ep, st) : tc_launch<AP, BNV, 3>(ap, blob, nkb, M, nt, ep, st);
+    int rc = DEFT_EINVAL;
+#define TC_CASE(BNV)                                                                                             \
+    case BNV:                                                                                                    \
+        rc = x1 ? tc_launch<AP, BNV, 1, EpiStd>(ap, blob, nkb, M, nt, splits, epi, st)                           \
+                : tc_launch<AP, BNV, 3, EpiStd>(ap, blob, nkb, M, nt, splits, epi, st);                          \
+        break;
     switch (bn) {
         TC_CASE(128)
         TC_CASE(64)
@@ -487,40 +684,62 @@ static int tc_dispatch(AP ap, const float* blob, int ldw, int K, int M, const Ep
         TC_CASE(16)
     }
 #undef TC_CASE
-    return DEFT_EINVAL;
+    if (rc != DEFT_OK || splits == 1) return rc;
+    size_t total = (size_t)M * (ep.Cout / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    DEFT_CHECK_LAUNCH("splitk_reduce");
+    return DEFT_OK;
 }
 
-int tc_conv_dispatch(const ConvAP& ap, const float* blob, int ldw, int K, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
+int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                     size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
         if (ap.c[i] % 4 != 0) return DEFT_EINVAL;
     TcConvAP t{};
     t.a = ap;
     t.K = K;
-    return tc_dispatch(t, blob, ldw, K, M, ep, flags, tc_tile_n(ldw), st);
+    return tc_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
 }
 
-int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int ldw, int K, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
-    if (ap.Cin % 32 != 0) return DEFT_EINVAL;
+int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                    size_t scratch_bytes, cudaStream_t st) {
+    if (ap.Cin % 32 != 0 || bn > 64) return DEFT_EINVAL;
     TcDcnAP t{};
     t.a = ap;
     t.K = K;
-    // the 36 KB corner table leaves room for 64-wide weight tiles only
-    int bn = tc_tile_n(ldw) > 64 ? 64 : tc_tile_n(ldw);
-    return tc_dispatch(t, blob, ldw, K, M, ep, flags, bn, st);
+    return tc_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
 }
 
-int tc_pair_dispatch(const PairAP& ap, const float* blob, int ldw, int K, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
+int tc_pair_dispatch(const PairAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
     TcPairAP t{};
     t.a = ap;
     t.K = K;
-    return tc_dispatch(t, blob, ldw, K, M, ep, flags, tc_tile_n(ldw), st);
+    return tc_dispatch(t, blob, bn, ldw, K, M, ep, flags, nullptr, 0, st);
+}
+
+int tc_heads_dispatch(const ConvAP& ap, const float* blob, int K, int M, const HeadsArgs& ha, unsigned flags, cudaStream_t st) {
+    if (blob == nullptr || ha.nheads < 1) return DEFT_EINVAL;
+    EpiHeads epi{};
+    epi.b1 = ha.b1; epi.w2 = ha.w2; epi.b2 = ha.b2; epi.HW = ha.HW;
+    for (int h = 0; h < ha.nheads; ++h) {
+        if (ha.c[h] > HEADS_MAXC) return DEFT_EINVAL;
+        epi.out[h] = ha.out[h]; epi.c[h] = ha.c[h]; epi.row0[h] = ha.row0[h];
+    }
+    TcConvAP t{};
+    t.a = ap;
+    t.K = K;
+    const int nkb = ceil_div(K, TC_BK);
+    if (flags & DEFT_FLAG_TF32X1) return tc_launch<TcConvAP, 256, 1, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
+    return tc_launch<TcConvAP, 256, 3, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
 }
 
 int tc_pack_weights(const float* wp, int ldw, int K, int bn, float* blob, cudaStream_t st) {
     int nkb = ceil_div(K, TC_BK), nt = ldw / bn;
     size_t total = (size_t)nt * nkb * bn * TC_BK;
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
     tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(wp, ldw, K, bn, nkb, nt, blob);
     DEFT_CHECK_LAUNCH("tc_pack_weights");
     return DEFT_OK;

@@ -46,14 +46,19 @@ class FramePlan:
         pad = (kh // 2) if pad is None else pad
         wp, ldw = packing.pack_conv(w)
         scale, shift = packing.fold_bn(self.sd, bnkey)
-        w_tc = ops.tc_pack(wp, ldw, wp.shape[0]) if self.flags & ops.FLAG_TENSORCORE else None
-        self.keep += [wp, scale, shift, w_tc]
         s0 = srcs[0]
         out = self._buf((s0.H + 2 * pad - kh) // stride + 1, (s0.W + 2 * pad - kw) // stride + 1, co)
+        M = self.N * out.H * out.W
+        w_tc, tc_bn = (None, 0)
+        if self.flags & ops.FLAG_TENSORCORE:
+            w_tc, tc_bn = ops.tc_pack(wp, ldw, wp.shape[0], M)
+            self._dcn_ws_bytes = max(self._dcn_ws_bytes, lib().deft_tc_scratch_bytes(ldw, wp.shape[0], M, ops.KIND_CONV))
+        self.keep += [wp, scale, shift, w_tc]
         self._rec("deft_conv2d_bn_act", ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
                   int_array([s.pitch for s in srcs]), len(srcs), self.N, s0.H, s0.W, wp.data_ptr(), ldw,
-                  None if w_tc is None else w_tc.data_ptr(), scale.data_ptr(), shift.data_ptr(), None if residual is None else residual.ptr, 0 if residual is None else residual.pitch,
-                  out.ptr, out.pitch, co, kh, kw, stride, pad, self.flags | (FLAG_RELU if relu else 0))
+                  None if w_tc is None else w_tc.data_ptr(), tc_bn, scale.data_ptr(), shift.data_ptr(),
+                  None if residual is None else residual.ptr, 0 if residual is None else residual.pitch,
+                  out.ptr, out.pitch, co, kh, kw, stride, pad, self.flags | (FLAG_RELU if relu else 0), "DCN_WS", "DCN_WS_BYTES")
         return out
 
     def _maxpool(self, a):
@@ -64,17 +69,15 @@ class FramePlan:
     def _deform(self, p, a):
         """DeformConv (dla.py:646-665): DCN + folded BN + ReLU."""
         pk = packing.pack_dcn(self.sd, p + ".conv", p + ".actf.0")
-        tcp = lambda k: None if k not in pk else pk[k].data_ptr()
-        if self.flags & ops.FLAG_TENSORCORE:
-            pk["w_tc"] = ops.tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], True)
-            pk["w_om_tc"] = ops.tc_pack(pk["w_om"], 32, 9 * pk["cin"], False)
+        tc = ops.dcn_tc_blobs(pk, self.N * a.H * a.W) if self.flags & ops.FLAG_TENSORCORE else (None, 0, None, 0)
+        tcp = lambda t: None if t is None else t.data_ptr()
         self.keep.append(pk)
         out = self._buf(a.H, a.W, pk["cout"])
         need = lib().deft_dcnv2_workspace_bytes(self.N, a.H, a.W, pk["cin"], pk["cout"])
         self._dcn_ws_bytes = max(self._dcn_ws_bytes, need)
         self._rec("deft_dcnv2_forward", a.ptr, a.pitch, self.N, a.H, a.W, pk["cin"], pk["w_om"].data_ptr(), pk["b_om"].data_ptr(),
-                  tcp("w_om_tc"), pk["w"].data_ptr(), pk["ldw"], tcp("w_tc"), pk["scale"].data_ptr(), pk["shift"].data_ptr(), out.ptr, out.pitch, pk["cout"],
-                  self.flags | FLAG_RELU, "DCN_WS", "DCN_WS_BYTES")
+                  tcp(tc[2]), tc[3], pk["w"].data_ptr(), pk["ldw"], tcp(tc[0]), tc[1], pk["scale"].data_ptr(), pk["shift"].data_ptr(),
+                  out.ptr, out.pitch, pk["cout"], self.flags | FLAG_RELU, "DCN_WS", "DCN_WS_BYTES")
         return out
 
     def _up_add(self, p, a, skip):
@@ -144,13 +147,14 @@ class FramePlan:
         self.feature_maps = base + ups + y
         # heads
         hp = packing.pack_heads(sd, self.heads)
-        if self.flags & ops.FLAG_TENSORCORE:
-            hp["w1_tc"] = ops.tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0])
-        self.keep.append(hp)
         feat = y[-1]
         hh, hw = feat.H, feat.W
+        fused = bool(self.flags & ops.FLAG_TENSORCORE) and max(hp["head_c"]) <= 16
+        if fused:     # one tcgen05 kernel: 3x3 conv + bias + ReLU + the 1x1 conv; the hidden map never reaches HBM
+            hp["w1_tc"], _ = ops.tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], N * hh * hw, ops.KIND_HEADS)
+        self.keep.append(hp)
         self.head_out = {h: torch.empty((N, c, hh, hw), dtype=torch.float32, device=self.device) for h, c in self.heads.items()}
-        ws_bytes = lib().deft_heads_workspace_bytes(N, hh, hw, len(self.heads), hp["head_conv"])
+        ws_bytes = 256 if fused else lib().deft_heads_workspace_bytes(N, hh, hw, len(self.heads), hp["head_conv"])
         self.heads_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         self._rec("deft_heads_forward", feat.ptr, feat.pitch, N, hh, hw, feat.C, hp["w1"].data_ptr(),
                   hp["w1_tc"].data_ptr() if "w1_tc" in hp else None, hp["b1"].data_ptr(),

@@ -63,15 +63,26 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def tc_pack(wp, ldw, K, for_dcn=False):
-    """Packed weight Wp[K][ldw] -> tcgen05 tile images (device blob); one kernel launch, done at load time."""
-    n = lib().deft_tc_blob_bytes(ldw, K, 1 if for_dcn else 0)
+KIND_CONV, KIND_DCN, KIND_HEADS = 0, 1, 2
+
+
+def tc_pack(wp, ldw, K, M, kind=KIND_CONV):
+    """Packed weight Wp[K][ldw] -> (tcgen05 tile-image blob, tile N) for an M-row problem; one kernel launch,
+    done at load time.  The returned bn must accompany the blob in every call."""
+    bn = lib().deft_tc_tile_n(ldw, M, kind)
+    n = lib().deft_tc_blob_bytes(ldw, K, bn)
     blob = torch.empty(n // 4, dtype=torch.float32, device=wp.device)
-    check(lib().deft_tc_pack_weights(wp.data_ptr(), ldw, K, 1 if for_dcn else 0, blob.data_ptr(), stream_ptr()), "tc_pack_weights")
-    return blob
+    check(lib().deft_tc_pack_weights(wp.data_ptr(), ldw, K, bn, blob.data_ptr(), stream_ptr()), "tc_pack_weights")
+    return blob, bn
 
 
-def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, residual=None, out=None, flags=0, w_tc=None):
+def tc_scratch(ldw, K, M, kind, device):
+    n = lib().deft_tc_scratch_bytes(ldw, K, M, kind)
+    return torch.empty(n, dtype=torch.uint8, device=device) if n else None
+
+
+def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, residual=None, out=None, flags=0, w_tc=None, tc_bn=0,
+                  ws=None):
     s0 = srcs[0]
     OH = (s0.H + 2 * pad - kh) // stride + 1
     OW = (s0.W + 2 * pad - kw) // stride + 1
@@ -79,12 +90,15 @@ def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, 
         out = NHWC.empty(s0.N, OH, OW, cout, s0.t.device)
     fl = flags | (FLAG_RELU if relu else 0)
     if (flags & FLAG_TENSORCORE) and w_tc is None:
-        w_tc = tc_pack(wp, ldw, wp.shape[0])
+        M = s0.N * OH * OW
+        w_tc, tc_bn = tc_pack(wp, ldw, wp.shape[0], M)
+        if ws is None:
+            ws = tc_scratch(ldw, wp.shape[0], M, KIND_CONV, s0.t.device)
     check(lib().deft_conv2d_bn_act(ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
                                    int_array([s.pitch for s in srcs]), len(srcs), s0.N, s0.H, s0.W, wp.data_ptr(), ldw,
-                                   _p(w_tc), _p(scale), _p(shift), None if residual is None else residual.ptr,
+                                   _p(w_tc), tc_bn, _p(scale), _p(shift), None if residual is None else residual.ptr,
                                    0 if residual is None else residual.pitch, out.ptr, out.pitch, cout, kh, kw, stride, pad,
-                                   fl, stream_ptr()), "conv2d_bn_act")
+                                   fl, _p(ws), 0 if ws is None else ws.numel(), stream_ptr()), "conv2d_bn_act")
     return out
 
 
@@ -115,13 +129,22 @@ def dcnv2_forward(a: NHWC, pk, relu, ws=None, out=None, flags=0):
     if out is None:
         out = NHWC.empty(a.N, a.H, a.W, pk["cout"], a.t.device)
     fl = flags | (FLAG_RELU if relu else 0)
-    if (flags & FLAG_TENSORCORE) and "w_tc" not in pk:
-        pk["w_tc"] = tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], True)
-        pk["w_om_tc"] = tc_pack(pk["w_om"], 32, 9 * pk["cin"], False)
+    tc = dcn_tc_blobs(pk, a.N * a.H * a.W) if (flags & FLAG_TENSORCORE) else (None, 0, None, 0)
     check(lib().deft_dcnv2_forward(a.ptr, a.pitch, a.N, a.H, a.W, pk["cin"], pk["w_om"].data_ptr(), pk["b_om"].data_ptr(),
-                                   _p(pk.get("w_om_tc")), pk["w"].data_ptr(), pk["ldw"], _p(pk.get("w_tc")), pk["scale"].data_ptr(), pk["shift"].data_ptr(), out.ptr,
-                                   out.pitch, pk["cout"], fl, ws.data_ptr(), ws.numel(), stream_ptr()), "dcnv2_forward")
+                                   _p(tc[2]), tc[3], pk["w"].data_ptr(), pk["ldw"], _p(tc[0]), tc[1], pk["scale"].data_ptr(),
+                                   pk["shift"].data_ptr(), out.ptr, out.pitch, pk["cout"], fl, ws.data_ptr(), ws.numel(), stream_ptr()),
+          "dcnv2_forward")
     return out
+
+
+def dcn_tc_blobs(pk, M):
+    """(w_tc, tc_bn, w_om_tc, om_bn) for an M-pixel problem, packed once and cached in the pack dict."""
+    cache = pk.setdefault("_tc", {})
+    if M not in cache:
+        w_tc, bn = tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], M, KIND_DCN)
+        w_om_tc, om_bn = tc_pack(pk["w_om"], 32, 9 * pk["cin"], M, KIND_CONV)
+        cache[M] = (w_tc, bn, w_om_tc, om_bn)
+    return cache[M]
 
 
 def upsample_add(a: NHWC, wp, f, skip=None, out=None):
@@ -141,7 +164,7 @@ def heads_forward(feat: NHWC, hp, outs=None, ws=None, flags=0):
     if outs is None:
         outs = [torch.empty((feat.N, c, feat.H, feat.W), dtype=torch.float32, device=feat.t.device) for c in hp["head_c"]]
     if (flags & FLAG_TENSORCORE) and "w1_tc" not in hp:
-        hp["w1_tc"] = tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0])
+        hp["w1_tc"], _ = tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], feat.N * feat.H * feat.W, KIND_HEADS)
     check(lib().deft_heads_forward(feat.ptr, feat.pitch, feat.N, feat.H, feat.W, feat.C, hp["w1"].data_ptr(), _p(hp.get("w1_tc")), hp["b1"].data_ptr(),
                                    hp["head_conv"], hp["w2"].data_ptr(), hp["b2"].data_ptr(), int_array(hp["head_c"]), nh,
                                    ptr_array([o.data_ptr() for o in outs]), flags, ws.data_ptr(), ws.numel(), stream_ptr()),
@@ -217,13 +240,19 @@ def afe_affinity(xp, counts, xn, m, P, pk, out=None, ws=None, flags=0):
         ws = torch.empty(lib().deft_afe_affinity_workspace_bytes(F, P, cemb), dtype=torch.uint8, device=dev)
     if out is None:
         out = torch.zeros((F, P, P + 1), dtype=torch.float32, device=dev)
-    if (flags & FLAG_TENSORCORE) and "tc" not in pk:
-        pk["tc"] = [tc_pack(pk[k], pk[k].shape[1], pk[k].shape[0]) for k in ("w1a", "w1b", "w2", "w3", "w4")]
-    tc = ptr_array([t.data_ptr() for t in pk["tc"]]) if "tc" in pk else None
+    tc, tcbn = None, None
+    if flags & FLAG_TENSORCORE:
+        cache = pk.setdefault("_tc", {})
+        if (F, P) not in cache:       # any valid tile works for any M; pick tiles for the nominal (full) problem sizes
+            nominal = {"w1a": F * P, "w1b": P, "w2": F * P * P, "w3": F * P * P, "w4": F * P * P}
+            cache[(F, P)] = [tc_pack(pk[k], pk[k].shape[1], pk[k].shape[0], nominal[k]) for k in ("w1a", "w1b", "w2", "w3", "w4")]
+        blobs = cache[(F, P)]
+        tc = ptr_array([b.data_ptr() for b, _ in blobs])
+        tcbn = int_array([bn for _, bn in blobs])
     check(lib().deft_afe_affinity(xp.data_ptr(), int_array(list(counts)), F, xn.data_ptr(), m, P, cemb, pk["w1a"].data_ptr(),
                                   pk["w1b"].data_ptr(), pk["sh1"].data_ptr(), pk["w2"].data_ptr(), pk["sc2"].data_ptr(),
                                   pk["sh2"].data_ptr(), pk["w3"].data_ptr(), pk["sc3"].data_ptr(), pk["sh3"].data_ptr(),
-                                  pk["w4"].data_ptr(), pk["b4"].data_ptr(), pk["w5"].data_ptr(), C.c_float(pk["b5"]), tc,
+                                  pk["w4"].data_ptr(), pk["b4"].data_ptr(), pk["w5"].data_ptr(), C.c_float(pk["b5"]), tc, tcbn,
                                   out.data_ptr(), flags, ws.data_ptr(), ws.numel(), stream_ptr()), "afe_affinity")
     return out
 

@@ -127,10 +127,9 @@ class FramePipeline:
         return out_host
 
     def count_launches(self):
-        """Kernel launches of one frame (our kernels only), by wrapping the C-ABI table once."""
-        n = self.plan.n_launches
-        n += sum(KERNELS_PER_CALL[k] for k in ("deft_sigmoid_output", "deft_decode", "deft_boxes_to_centres", "deft_afe_extract", "deft_afe_affinity"))
-        n += sum(1 for h in _REG_HEADS if h in self.model.heads)
-        if self.lstm is not None:
-            n += 1
-        return n
+        """Kernel launches of one frame (our kernels only): the library counts every launch it makes
+        (deft_launch_count); one eager frame is run between two readings."""
+        before = _lib.lib().deft_launch_count()
+        self._body()
+        torch.cuda.synchronize(self.device)
+        return int(_lib.lib().deft_launch_count() - before)

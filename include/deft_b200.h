@@ -47,13 +47,19 @@ int deft_version(void);
 const char* deft_last_error(void);
 /* 1 if the current device is sm_100 (B200); the product path refuses to run elsewhere. */
 int deft_device_ok(void);
+/* Total CUDA kernels this library has launched in this process (diagnostics / bench.py's gpu_launches). */
+unsigned long long deft_launch_count(void);
 
 /* ---- tcgen05 weight images: a packed weight Wp[K][ldw] re-laid as ready-to-copy shared-memory tiles
- * ([n_tile][k_block][hi|lo][BN x 32] fp32, SWIZZLE_128B, split x = hi + lo for 3xTF32).  for_dcn selects
- * the N tile of the deformable kernel (<= 64, its corner table needs the shared memory). */
-int deft_tc_tile_n(int ldw, int for_dcn);
-size_t deft_tc_blob_bytes(int ldw, int K, int for_dcn);
-int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int for_dcn, float* blob, deft_stream_t s);
+ * ([n_tile][k_block][hi|lo][bn x 32] fp32, SWIZZLE_128B, split x = hi + lo for 3xTF32).
+ * kind: 0 = conv / plain GEMM, 1 = deformable gather (bn <= 64), 2 = fused heads (bn = 256).
+ * deft_tc_tile_n picks bn for an M-row problem; the same bn must be passed to every call that uses the blob.
+ * deft_tc_scratch_bytes: split-K scratch the engine wants for that problem (0 = none; optional, without it
+ * small-M layers simply run unsplit). */
+int deft_tc_tile_n(int ldw, int M, int kind);
+size_t deft_tc_blob_bytes(int ldw, int K, int bn);
+int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, float* blob, deft_stream_t s);
+size_t deft_tc_scratch_bytes(int ldw, int K, int M, int kind);
 
 /* ---- layout converters at the reference's NCHW boundary ------------------------------------ */
 int deft_nchw_to_nhwc(const float* src, float* dst, int dst_pitch, int N, int C, int H, int W, deft_stream_t s);
@@ -64,12 +70,13 @@ int deft_nhwc_to_nchw(const float* src, int src_pitch, float* dst, int N, int C,
  *   out[p,co] = act( scale[co]*sum_k A[p,k]*Wp[k,co] + shift[co] + residual[p,co] )
  * Wp packed [KH*KW*Cin_total][ldw], k = (ky*KW+kx)*Cin_total + ci, ldw = Cout rounded up to 16.
  * Cin of every source must be a multiple of 16.  residual may be NULL.
- * w_tc: the same weights as tcgen05 tile images (deft_tc_pack_weights(..., for_dcn=0)) or NULL; used when
- * DEFT_FLAG_TENSORCORE is set, otherwise (or for uncovered shapes) the fp32 SIMT engine runs. */
+ * w_tc / tc_bn: the same weights as tcgen05 tile images (deft_tc_pack_weights, kind 0) or NULL; used when
+ * DEFT_FLAG_TENSORCORE is set, otherwise (or for uncovered shapes) the fp32 SIMT engine runs.
+ * ws: optional split-K scratch (deft_tc_scratch_bytes) or NULL. */
 int deft_conv2d_bn_act(const float* const* srcs_host, const int* src_c_host, const int* src_pitch_host, int nsrc,
-                       int N, int H, int W, const float* w_packed, int ldw, const float* w_tc, const float* scale,
+                       int N, int H, int W, const float* w_packed, int ldw, const float* w_tc, int tc_bn, const float* scale,
                        const float* shift, const float* residual, int res_pitch, float* out, int out_pitch, int Cout,
-                       int KH, int KW, int stride, int pad, unsigned flags, deft_stream_t s);
+                       int KH, int KW, int stride, int pad, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
 
 /* ---- a2: the 7x7 stem on the raw NCHW image (dla.py:301-305): x[N,3,H,W] -> NHWC [N,H,W,16].
  * w_packed [7*7*3][16] (k = (ky*7+kx)*3+ci). */
@@ -85,12 +92,12 @@ int deft_maxpool2x2(const float* in, int in_pitch, float* out, int out_pitch, in
  *   y[p,co] = act( scale[co]*sum_{k,ci} Wp[k*Cin+ci,co]*mask_k(p)*bilinear(x[:,ci]; p+tap_k+off_k(p)) + shift[co] )
  * (bias and BN are folded into scale/shift by the packer; scale=1, shift=bias gives the bare op).
  * w_om_packed [9*Cin][32] (27 real columns), b_om[32]; Wp [9*Cin][ldw].
- * w_om_tc / w_tc: tcgen05 tile images of the two weights (for_dcn = 0 / 1) or NULL.
+ * w_om_tc,om_bn / w_tc,tc_bn: tcgen05 tile images of the two weights (kind 0 / kind 1) or NULL.
  * ws: >= deft_dcnv2_workspace_bytes() (holds the [P,32] offset/mask map). */
 size_t deft_dcnv2_workspace_bytes(int N, int H, int W, int Cin, int Cout);
 int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin,
-                       const float* w_om_packed, const float* b_om, const float* w_om_tc, const float* w_packed, int ldw,
-                       const float* w_tc, const float* scale, const float* shift, float* y, int y_pitch, int Cout,
+                       const float* w_om_packed, const float* b_om, const float* w_om_tc, int om_bn, const float* w_packed, int ldw,
+                       const float* w_tc, int tc_bn, const float* scale, const float* shift, float* y, int y_pitch, int Cout,
                        unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
 
 /* ---- a4: IDAUp's depthwise ConvTranspose2d(k=2f,s=f,p=f/2,groups=C) fused with the following
@@ -105,7 +112,7 @@ int deft_upsample_add(const float* x, int x_pitch, const float* w_packed, const 
  * outs_host[h] -> plain NCHW [N,C_h,H,W].  ws holds the hidden map. */
 size_t deft_heads_workspace_bytes(int N, int H, int W, int nheads, int head_conv);
 int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, int Cin,
-                       const float* w1_packed, const float* w1_tc, const float* b1, int head_conv,
+                       const float* w1_packed, const float* w1_tc /* kind 2, bn 256 */, const float* b1, int head_conv,
                        const float* w2, const float* b2, const int* head_c_host, int nheads,
                        float* const* outs_host, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
 
@@ -151,7 +158,7 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
                       const float* w2, const float* sc2, const float* sh2,
                       const float* w3, const float* sc3, const float* sh3,
                       const float* w4, const float* b4, const float* w5, float b5,
-                      const float* const* tc_host /* {w1a,w1b,w2,w3,w4} tile images or NULL */,
+                      const float* const* tc_host /* {w1a,w1b,w2,w3,w4} tile images or NULL */, const int* tc_bn_host,
                       float* out, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
 
 /* ---- a10: KalmanFilterLSTM.predict (kalman_filter_lstm.py:65-78) for T independent tracks in one

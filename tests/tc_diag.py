@@ -28,6 +28,10 @@ CASES = {
     "dcn_64_64": ("dcn", 64, 64, 3, 1, 21, 30, 1),
     "dcn_512_256": ("dcn", 512, 256, 3, 1, 5, 7, 2),
     "dcn_128_128": ("dcn", 128, 128, 3, 1, 13, 10, 1),
+    "heads_mot": ("heads", 64, 0, 3, 1, 21, 30, 2),
+    "heads_nusc": ("heads_nusc", 64, 0, 3, 1, 21, 30, 1),
+    "big_heads_mot": ("heads", 64, 0, 3, 1, 152, 272, 1),
+    "c3x3_256_256_l4": ("conv", 256, 256, 3, 1, 38, 68, 1),
     "big_c3x3_64_64": ("conv", 64, 64, 3, 1, 152, 272, 1),
     "big_dcn_64_64": ("dcn", 64, 64, 3, 1, 152, 272, 1),
 }
@@ -58,6 +62,15 @@ def run_case(name):
             resid = ops.as_nhwc(spec.make_input((N, cout, OH, OW), tag="res").to(dev))
             out = ops.conv2d_bn_act(srcs, wp, ldw, sc, sh, cout, k, k, stride, k // 2, True, residual=resid, flags=flags)
             torch.manual_seed(0)
+        elif kind.startswith("heads"):
+            heads = spec.NUSC_HEADS if kind == "heads_nusc" else spec.MOT_HEADS
+            sd = spec.make_state_dict({kk: v for kk, v in spec.dlaseg_spec(heads).items() if kk.split(".")[0] in heads}, seed=21)
+            hp = packing.pack_heads({kk: v.to(dev) for kk, v in sd.items()}, heads)
+            feat = ops.as_nhwc(spec.make_input((N, 64, H, W), tag="hf").to(dev))
+            outs = ops.heads_forward(feat, hp, flags=flags)
+            torch.cuda.synchronize()
+            res[label] = torch.cat([o.float().cpu() for o in outs], 1)
+            continue
         else:
             sp = {}
             spec._deform(sp, "d", cin, cout)
