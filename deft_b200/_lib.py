@@ -22,7 +22,7 @@ _SIGS = {
     "deft_launch_count": (C.c_ulonglong, []),
     "deft_tc_tile_n": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_blob_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "deft_tc_pack_weights": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
+    "deft_tc_pack_weights": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),
     "deft_tc_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "deft_nchw_to_nhwc": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
     "deft_nhwc_to_nchw": (C.c_int, [c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp]),
@@ -44,8 +44,9 @@ _SIGS = {
                               c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
     "deft_gather_feat": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_fp, c_fp]),
     "deft_boxes_to_centres": (C.c_int, [c_fp, C.c_int, C.c_float, C.c_float, c_fp, c_fp]),
+    "deft_afe_extract_workspace_bytes": (C.c_size_t, [C.c_int]),
     "deft_afe_extract": (C.c_int, [c_ptr_p, c_int_p, c_int_p, c_int_p, c_int_p, c_ptr_p, c_ptr_p, c_int_p, c_fp, C.c_int, c_fp,
-                                   C.c_int, c_fp]),
+                                   C.c_int, c_fp, C.c_size_t, c_fp]),
     "deft_afe_affinity_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "deft_afe_affinity": (C.c_int, [c_fp, c_int_p, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                     c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float, c_ptr_p, c_int_p, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),

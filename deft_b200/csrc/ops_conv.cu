@@ -235,9 +235,9 @@ size_t deft_tc_blob_bytes(int ldw, int K, int bn) {
     return align_up(tc_blob_floats(ldw, K, bn) * sizeof(float), 256);
 }
 
-int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, float* blob, deft_stream_t s) {
-    DEFT_REQUIRE(w_packed && blob && ldw > 0 && bn > 0 && ldw % bn == 0 && K > 0, "tc_pack_weights: bad args");
-    return tc_pack_weights(w_packed, ldw, K, bn, blob, to_stream(s));
+int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, int taps, float* blob, deft_stream_t s) {
+    DEFT_REQUIRE(w_packed && blob && ldw > 0 && bn > 0 && ldw % bn == 0 && K > 0 && taps >= 1, "tc_pack_weights: bad args");
+    return tc_pack_weights(w_packed, ldw, K, bn, taps, blob, to_stream(s));
 }
 
 size_t deft_tc_scratch_bytes(int ldw, int K, int M, int kind) { return tc_splitk_scratch_bytes(ldw, K, M, kind); }

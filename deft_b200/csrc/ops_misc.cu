@@ -1,5 +1,5 @@
 // Non-conv entry points: sigmoid_output, CenterNet decode (NMS + exact two-stage top-K + gathers),
-// AFE sparse embedding extractor, AFE pairwise-MLP affinity + dual softmax, batched LSTM step.
+// AFE pairwise-MLP affinity + dual softmax, batched LSTM step.  (The AFE extractor lives in ops_afe.cu.)
 #include "igemm_simt.cuh"
 #include "tc_engine.cuh"
 
@@ -161,72 +161,6 @@ __global__ void boxes_to_centres_kernel(const float* __restrict__ b, int N, floa
     float x1 = b[i * 4 + 0], y1 = b[i * 4 + 1], x2 = b[i * 4 + 2], y2 = b[i * 4 + 3];
     c[i * 2 + 0] = (2.f * (x1 / W) + (x2 - x1) / W) - 1.0f;
     c[i * 2 + 1] = (2.f * (y1 / H) + (y2 - y1) / H) - 1.0f;
-}
-
-// ================================================================================================
-// a7: AFE sparse extractor.  grid (N, 13), 256 threads: thread = (corner 0..3, out channel 0..63).
-struct AfeArgs {
-    const float* map[DEFT_AFE_MAPS];
-    const float* w[DEFT_AFE_MAPS];
-    const float* b[DEFT_AFE_MAPS];
-    int pitch[DEFT_AFE_MAPS], C[DEFT_AFE_MAPS], H[DEFT_AFE_MAPS], W[DEFT_AFE_MAPS], Co[DEFT_AFE_MAPS], off[DEFT_AFE_MAPS];
-    int Cemb, align_corners;
-};
-__global__ void __launch_bounds__(256) afe_extract_kernel(AfeArgs a, const float* __restrict__ centres, float* __restrict__ emb) {
-    __shared__ __align__(16) float patch[16 * 512];
-    __shared__ float res[4][64];
-    __shared__ float cw[4];
-    const int n = blockIdx.x, k = blockIdx.y, tid = threadIdx.x;
-    const int C = a.C[k], H = a.H[k], W = a.W[k], Co = a.Co[k], pitch = a.pitch[k];
-    float gx = centres[n * 2 + 0], gy = centres[n * 2 + 1];
-    float ix, iy;
-    if (a.align_corners) { ix = ((gx + 1.f) / 2.f) * (float)(W - 1); iy = ((gy + 1.f) / 2.f) * (float)(H - 1); }
-    else { ix = ((gx + 1.f) * (float)W - 1.f) / 2.f; iy = ((gy + 1.f) * (float)H - 1.f) / 2.f; }
-    ix = fminf((float)(W - 1), fmaxf(ix, 0.f));   // padding_mode = border
-    iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
-    float fx = floorf(ix), fy = floorf(iy);
-    int x0 = (int)fx, y0 = (int)fy;
-    if (tid == 0) {
-        float tx = ix - fx, ty = iy - fy;   // (ix - x0), (iy - y0); x1 - ix = 1 - tx
-        cw[0] = (fx + 1.f - ix) * (fy + 1.f - iy);  // nw
-        cw[1] = tx * (fy + 1.f - iy);               // ne
-        cw[2] = (fx + 1.f - ix) * ty;               // sw
-        cw[3] = tx * ty;                            // se
-    }
-    // 4x4 pixel patch around (y0-1..y0+2, x0-1..x0+2), zero outside the map (conv zero padding)
-    const float* m = a.map[k];
-    const int C4 = C / 4;
-    for (int i = tid; i < 16 * C4; i += 256) {
-        int pp = i / C4, c4 = i - pp * C4;
-        int yy = y0 - 1 + (pp >> 2), xx = x0 - 1 + (pp & 3);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = ldg4(m + ((size_t)yy * W + xx) * pitch + c4 * 4);
-        *reinterpret_cast<float4*>(&patch[pp * C + c4 * 4]) = v;
-    }
-    __syncthreads();
-    const int corner = tid >> 6, o = tid & 63;
-    const int cy = corner >> 1, cx = corner & 1;
-    const bool inb = (y0 + cy <= H - 1) && (x0 + cx <= W - 1);
-    float acc = 0.f;
-    if (o < Co && inb) {
-        const float* wk = a.w[k];
-        acc = a.b[k][o];
-        for (int tap = 0; tap < 9; ++tap) {
-            int ky = tap / 3, kx = tap - ky * 3;
-            const float* pr = &patch[((cy + ky) * 4 + (cx + kx)) * C];
-            const float* wr = wk + (size_t)tap * C * Co + o;
-            for (int ci = 0; ci < C; ci += 4) {
-                float4 pv = *reinterpret_cast<const float4*>(pr + ci);
-                float w0 = __ldg(wr + (size_t)(ci + 0) * Co), w1 = __ldg(wr + (size_t)(ci + 1) * Co);
-                float w2 = __ldg(wr + (size_t)(ci + 2) * Co), w3 = __ldg(wr + (size_t)(ci + 3) * Co);
-                acc += pv.x * w0; acc += pv.y * w1; acc += pv.z * w2; acc += pv.w * w3;
-            }
-        }
-        acc = fmaxf(acc, 0.f);
-    }
-    res[corner][o] = (o < Co && inb) ? acc * cw[corner] : 0.f;
-    __syncthreads();
-    if (tid < Co) emb[(size_t)n * a.Cemb + a.off[k] + tid] = res[0][tid] + res[1][tid] + res[2][tid] + res[3][tid];
 }
 
 // ================================================================================================
@@ -420,26 +354,6 @@ int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* ce
     DEFT_REQUIRE(boxes && centres && N > 0 && W > 0 && H > 0, "boxes_to_centres: bad args");
     boxes_to_centres_kernel<<<ceil_div(N, 128), 128, 0, to_stream(s)>>>(boxes, N, W, H, centres);
     DEFT_CHECK_LAUNCH("boxes_to_centres");
-    return DEFT_OK;
-}
-
-int deft_afe_extract(const float* const* maps, const int* pitch, const int* C, const int* H, const int* W,
-                     const float* const* selw, const float* const* selb, const int* Co, const float* centres, int N,
-                     float* emb, int align_corners, deft_stream_t s) {
-    DEFT_REQUIRE(maps && pitch && C && H && W && selw && selb && Co && centres && emb && N > 0, "afe_extract: bad args");
-    AfeArgs a{};
-    int off = 0;
-    for (int k = 0; k < DEFT_AFE_MAPS; ++k) {
-        DEFT_REQUIRE(maps[k] && selw[k] && selb[k] && C[k] % 4 == 0 && C[k] <= 512 && Co[k] <= 64 && pitch[k] % 4 == 0,
-                     "afe_extract: map %d needs C%%4==0, C<=512, Co<=64", k);
-        a.map[k] = maps[k]; a.w[k] = selw[k]; a.b[k] = selb[k];
-        a.pitch[k] = pitch[k]; a.C[k] = C[k]; a.H[k] = H[k]; a.W[k] = W[k]; a.Co[k] = Co[k]; a.off[k] = off;
-        off += Co[k];
-    }
-    a.Cemb = off;
-    a.align_corners = align_corners;
-    afe_extract_kernel<<<dim3(N, DEFT_AFE_MAPS), 256, 0, to_stream(s)>>>(a, centres, emb);
-    DEFT_CHECK_LAUNCH("afe_extract");
     return DEFT_OK;
 }
 

@@ -128,6 +128,7 @@ __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(
 struct TcConvAP {
     ConvAP a;
     int K;
+    int perm_taps;       // 0 = tap-major K order, else KH*KW with channel-block-major order (tc_k_perm_taps)
     static constexpr int kExtraSmemBytes = 0;
     static constexpr int RAW = 4;
     static constexpr int DEPTH = 2;
@@ -148,15 +149,23 @@ struct TcConvAP {
         }
     }
     __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
-        int k = kb * TC_BK + (threadIdx.x & 7) * 4;
-        int tap = k / a.Ctot;
-        int cc = k - tap * a.Ctot;
+        int tap, cc;
+        bool kok = true;
+        if (perm_taps) {          // K order = (32-channel block, tap, channel): the 9 taps of a block hit L1
+            const int cb = kb / perm_taps;
+            tap = kb - cb * perm_taps;
+            cc = cb * TC_BK + (threadIdx.x & 7) * 4;
+        } else {                  // K order = (tap, channel)
+            const int k = kb * TC_BK + (threadIdx.x & 7) * 4;
+            tap = k / a.Ctot;
+            cc = k - tap * a.Ctot;
+            kok = k < K;
+        }
         int ky = tap / a.KW, kx = tap - ky * a.KW;
         int s = 0;
         while (s < a.nsrc - 1 && cc >= a.c[s]) { cc -= a.c[s]; ++s; }
         const float* base = a.src[s];
         const int pitch = a.pitch[s];
-        const bool kok = k < K;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int iy = oy_[i] + ky;
@@ -218,9 +227,10 @@ struct TcDcnAP {
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
-        const int kbpt = a.Cin / TC_BK;                 // k-blocks per tap (Cin % 32 == 0)
-        const int tap = kb / kbpt;
-        const int cc = (kb - tap * kbpt) * TC_BK + (threadIdx.x & 7) * 4;
+        // K order = (32-channel block, tap, channel): 9 consecutive k-blocks re-read the same neighbourhood -> L1 hits
+        const int cb = kb / 9;
+        const int tap = kb - cb * 9;
+        const int cc = cb * TC_BK + (threadIdx.x & 7) * 4;
         const float* x = a.x + cc;
         const int pitch = a.pitch;
 #pragma unroll
@@ -233,7 +243,7 @@ struct TcDcnAP {
         }
     }
     __device__ __forceinline__ void combine(int kb, const float4 (&raw)[RAW], float4 (&v)[4]) const {
-        const int tap = kb / (a.Cin / TC_BK);
+        const int tap = kb % 9;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 w = tabW_[((threadIdx.x >> 3) + 32 * i) * 9 + tap];
@@ -580,8 +590,11 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 // Weight packing: SIMT layout Wp[K][ldw] -> [n_tiles][nkb][hi|lo][BN rows x 128 B swizzled], split hi/lo.
-__global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, int K, int BN, int nkb, int n_tiles, float* __restrict__ blob) {
+// perm_taps > 0: the blob's K order is (32-channel block, tap, channel) instead of (tap, channel) -- see tc_k_perm_taps.
+__global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, int K, int BN, int nkb, int n_tiles, int perm_taps,
+                                       float* __restrict__ blob) {
     size_t total = (size_t)n_tiles * nkb * BN * TC_BK;
+    const int ctot = perm_taps ? K / perm_taps : 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int kk = (int)(i % TC_BK);
         size_t t = i / TC_BK;
@@ -590,6 +603,10 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, in
         int kb = (int)(t % nkb);
         int nt = (int)(t / nkb);
         int k = kb * TC_BK + kk, co = nt * BN + n;
+        if (perm_taps) {
+            int cb = kb / perm_taps, tap = kb - cb * perm_taps;
+            k = tap * ctot + cb * TC_BK + kk;
+        }
         float w = (k < K && co < ldw) ? wp[(size_t)k * ldw + co] : 0.f;
         float hi = tf32_rna(w);
         float lo = tf32_rna(w - hi);
@@ -603,6 +620,10 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, in
 // ------------------------------------------------------------------------------------------------ host
 // Tile-N choice.  Depends only on (ldw, M, kind) so the packer and the dispatcher always agree; the chosen
 // value also travels explicitly with every call (tc_bn).
+// K permutation rule shared by the packer and every dispatcher: multi-tap convs whose channel count is a
+// multiple of 32 run channel-block-major (returns the tap count), everything else tap-major (returns 0).
+int tc_k_perm_taps(int K, int taps) { return (taps > 1 && K % taps == 0 && (K / taps) % TC_BK == 0) ? taps : 0; }
+
 int tc_pick_bn(int ldw, int M, int kind) {
     if (kind == TC_KIND_HEADS) return 256;
     const int max_bn = (kind == TC_KIND_DCN) ? 64 : 128;
@@ -700,6 +721,7 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
     TcConvAP t{};
     t.a = ap;
     t.K = K;
+    t.perm_taps = tc_k_perm_taps(K, ap.KH * ap.KW);
     return tc_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
 }
 
@@ -730,17 +752,18 @@ int tc_heads_dispatch(const ConvAP& ap, const float* blob, int K, int M, const H
     TcConvAP t{};
     t.a = ap;
     t.K = K;
+    t.perm_taps = tc_k_perm_taps(K, ap.KH * ap.KW);
     const int nkb = ceil_div(K, TC_BK);
     if (flags & DEFT_FLAG_TF32X1) return tc_launch<TcConvAP, 256, 1, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
     return tc_launch<TcConvAP, 256, 3, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
 }
 
-int tc_pack_weights(const float* wp, int ldw, int K, int bn, float* blob, cudaStream_t st) {
+int tc_pack_weights(const float* wp, int ldw, int K, int bn, int taps, float* blob, cudaStream_t st) {
     int nkb = ceil_div(K, TC_BK), nt = ldw / bn;
     size_t total = (size_t)nt * nkb * bn * TC_BK;
     int blocks = (int)((total + 255) / 256);
     if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
-    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(wp, ldw, K, bn, nkb, nt, blob);
+    tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(wp, ldw, K, bn, nkb, nt, tc_k_perm_taps(K, taps), blob);
     DEFT_CHECK_LAUNCH("tc_pack_weights");
     return DEFT_OK;
 }

@@ -20,7 +20,8 @@ struct HeadsArgs {
 int tc_pick_bn(int ldw, int M, int kind);                // N tile for a weight of width ldw on an M-row problem
 size_t tc_blob_floats(int ldw, int K, int bn);           // size of the packed hi/lo weight-tile blob
 size_t tc_splitk_scratch_bytes(int ldw, int K, int M, int kind);
-int tc_pack_weights(const float* wp, int ldw, int K, int bn, float* blob, cudaStream_t st);
+int tc_k_perm_taps(int K, int taps);                     // K-order rule shared by packer and dispatchers
+int tc_pack_weights(const float* wp, int ldw, int K, int bn, int taps, float* blob, cudaStream_t st);
 int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                      size_t scratch_bytes, cudaStream_t st);
 int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,

@@ -51,7 +51,7 @@ class FramePlan:
         M = self.N * out.H * out.W
         w_tc, tc_bn = (None, 0)
         if self.flags & ops.FLAG_TENSORCORE:
-            w_tc, tc_bn = ops.tc_pack(wp, ldw, wp.shape[0], M)
+            w_tc, tc_bn = ops.tc_pack(wp, ldw, wp.shape[0], M, taps=kh * kw)
             self._dcn_ws_bytes = max(self._dcn_ws_bytes, lib().deft_tc_scratch_bytes(ldw, wp.shape[0], M, ops.KIND_CONV))
         self.keep += [wp, scale, shift, w_tc]
         self._rec("deft_conv2d_bn_act", ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
@@ -151,7 +151,7 @@ class FramePlan:
         hh, hw = feat.H, feat.W
         fused = bool(self.flags & ops.FLAG_TENSORCORE) and max(hp["head_c"]) <= 16
         if fused:     # one tcgen05 kernel: 3x3 conv + bias + ReLU + the 1x1 conv; the hidden map never reaches HBM
-            hp["w1_tc"], _ = ops.tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], N * hh * hw, ops.KIND_HEADS)
+            hp["w1_tc"], _ = ops.tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], N * hh * hw, ops.KIND_HEADS, taps=9)
         self.keep.append(hp)
         self.head_out = {h: torch.empty((N, c, hh, hw), dtype=torch.float32, device=self.device) for h, c in self.heads.items()}
         ws_bytes = 256 if fused else lib().deft_heads_workspace_bytes(N, hh, hw, len(self.heads), hp["head_conv"])

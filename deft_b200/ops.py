@@ -66,13 +66,14 @@ def _p(t):
 KIND_CONV, KIND_DCN, KIND_HEADS = 0, 1, 2
 
 
-def tc_pack(wp, ldw, K, M, kind=KIND_CONV):
+def tc_pack(wp, ldw, K, M, kind=KIND_CONV, taps=1):
     """Packed weight Wp[K][ldw] -> (tcgen05 tile-image blob, tile N) for an M-row problem; one kernel launch,
-    done at load time.  The returned bn must accompany the blob in every call."""
+    done at load time.  `taps` = KH*KW of the conv that will consume it (its K order is channel-block-major when
+    the channel count allows).  The returned bn must accompany the blob in every call."""
     bn = lib().deft_tc_tile_n(ldw, M, kind)
     n = lib().deft_tc_blob_bytes(ldw, K, bn)
     blob = torch.empty(n // 4, dtype=torch.float32, device=wp.device)
-    check(lib().deft_tc_pack_weights(wp.data_ptr(), ldw, K, bn, blob.data_ptr(), stream_ptr()), "tc_pack_weights")
+    check(lib().deft_tc_pack_weights(wp.data_ptr(), ldw, K, bn, taps, blob.data_ptr(), stream_ptr()), "tc_pack_weights")
     return blob, bn
 
 
@@ -91,7 +92,7 @@ def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, 
     fl = flags | (FLAG_RELU if relu else 0)
     if (flags & FLAG_TENSORCORE) and w_tc is None:
         M = s0.N * OH * OW
-        w_tc, tc_bn = tc_pack(wp, ldw, wp.shape[0], M)
+        w_tc, tc_bn = tc_pack(wp, ldw, wp.shape[0], M, taps=kh * kw)
         if ws is None:
             ws = tc_scratch(ldw, wp.shape[0], M, KIND_CONV, s0.t.device)
     check(lib().deft_conv2d_bn_act(ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
@@ -141,8 +142,8 @@ def dcn_tc_blobs(pk, M):
     """(w_tc, tc_bn, w_om_tc, om_bn) for an M-pixel problem, packed once and cached in the pack dict."""
     cache = pk.setdefault("_tc", {})
     if M not in cache:
-        w_tc, bn = tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], M, KIND_DCN)
-        w_om_tc, om_bn = tc_pack(pk["w_om"], 32, 9 * pk["cin"], M, KIND_CONV)
+        w_tc, bn = tc_pack(pk["w"], pk["ldw"], 9 * pk["cin"], M, KIND_DCN, taps=9)
+        w_om_tc, om_bn = tc_pack(pk["w_om"], 32, 9 * pk["cin"], M, KIND_CONV, taps=9)
         cache[M] = (w_tc, bn, w_om_tc, om_bn)
     return cache[M]
 
@@ -164,7 +165,7 @@ def heads_forward(feat: NHWC, hp, outs=None, ws=None, flags=0):
     if outs is None:
         outs = [torch.empty((feat.N, c, feat.H, feat.W), dtype=torch.float32, device=feat.t.device) for c in hp["head_c"]]
     if (flags & FLAG_TENSORCORE) and "w1_tc" not in hp:
-        hp["w1_tc"], _ = tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], feat.N * feat.H * feat.W, KIND_HEADS)
+        hp["w1_tc"], _ = tc_pack(hp["w1"], hp["w1"].shape[1], hp["w1"].shape[0], feat.N * feat.H * feat.W, KIND_HEADS, taps=9)
     check(lib().deft_heads_forward(feat.ptr, feat.pitch, feat.N, feat.H, feat.W, feat.C, hp["w1"].data_ptr(), _p(hp.get("w1_tc")), hp["b1"].data_ptr(),
                                    hp["head_conv"], hp["w2"].data_ptr(), hp["b2"].data_ptr(), int_array(hp["head_c"]), nh,
                                    ptr_array([o.data_ptr() for o in outs]), flags, ws.data_ptr(), ws.numel(), stream_ptr()),
@@ -217,17 +218,19 @@ def boxes_to_centres(boxes, W, H, out=None):
     return out
 
 
-def afe_extract(maps, sel_w, sel_b, sel_co, centres, align_corners=False, out=None):
+def afe_extract(maps, sel_w, sel_b, sel_co, centres, align_corners=False, out=None, ws=None):
     """maps: 13 NHWC handles (batch 1); centres [N,2] device tensor -> emb [N, Cemb]."""
     N = centres.shape[0]
     cemb = sum(sel_co)
     if out is None:
         out = torch.empty((N, cemb), dtype=torch.float32, device=centres.device)
+    if ws is None:
+        ws = torch.empty(lib().deft_afe_extract_workspace_bytes(N), dtype=torch.uint8, device=centres.device)
     check(lib().deft_afe_extract(ptr_array([m.ptr for m in maps]), int_array([m.pitch for m in maps]),
                                  int_array([m.C for m in maps]), int_array([m.H for m in maps]), int_array([m.W for m in maps]),
                                  ptr_array([w.data_ptr() for w in sel_w]), ptr_array([b.data_ptr() for b in sel_b]),
                                  int_array(sel_co), centres.data_ptr(), N, out.data_ptr(), 1 if align_corners else 0,
-                                 stream_ptr()), "afe_extract")
+                                 ws.data_ptr(), ws.numel(), stream_ptr()), "afe_extract")
     return out
 
 

@@ -43,6 +43,7 @@ class FramePipeline:
         self.head = 0
         self.aff = torch.zeros((self.F, self.P, self.P + 1), dtype=torch.float32, device=dev)
         self.aff_ws = torch.empty(_lib.lib().deft_afe_affinity_workspace_bytes(self.F, self.P, self.cemb), dtype=torch.uint8, device=dev)
+        self.ext_ws = torch.empty(_lib.lib().deft_afe_extract_workspace_bytes(self.K), dtype=torch.uint8, device=dev)
         self.dec_ws = None
         if lstm is not None:
             fin = lstm.model.fin
@@ -53,6 +54,7 @@ class FramePipeline:
         self.x = self.plan.x_in                   # the plan's static input slot: no extra device copy per frame
         self.graph = None
         self.out = None
+        self._copy_stream, self._stage_idx = None, 0
         self.use_cuda_graph = use_cuda_graph
 
     # ------------------------------------------------------------------------------------------
@@ -72,7 +74,8 @@ class FramePipeline:
         oh, ow = hm.shape[2], hm.shape[3]
         centres = ops.boxes_to_centres(d["bboxes"].view(-1, 4), float(ow), float(oh))
         pk = self.model.AFE.packed()
-        emb = ops.afe_extract(self.plan.feature_maps, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres, self.model.AFE.align_corners)
+        emb = ops.afe_extract(self.plan.feature_maps, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres, self.model.AFE.align_corners,
+                              ws=self.ext_ws)
         ops.afe_affinity(self.memory, self.counts, emb, self.K, self.P, pk["mlp"], out=self.aff, ws=self.aff_ws, flags=self.model.AFE._flags)
         res["embeddings"] = emb
         res["affinity"] = self.aff
@@ -118,7 +121,26 @@ class FramePipeline:
         """End-to-end frame through the public API: pinned host image in, host results out
         (H2D of the frame, D2H of detections + affinity -- the copies the reference makes at
         detector.py:150,545-547 and AFE.py:154-158)."""
-        self.x.copy_(image_host, non_blocking=True)
+        # The upload runs on its own stream into a 2-deep staging ring, so the H2D of frame t+1 overlaps the
+        # kernels of frame t whenever the caller does not synchronise between steps (results land in pinned
+        # memory asynchronously; synchronise the stream / device before reading them).
+        cur = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [torch.empty_like(self.x) for _ in range(2)]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._stage_free:
+                e.record(cur)
+        j = self._stage_idx
+        self._stage_idx ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[j])
+            self._stage[j].copy_(image_host, non_blocking=True)
+            self._stage_ready[j].record(self._copy_stream)
+        cur.wait_event(self._stage_ready[j])
+        self.x.copy_(self._stage[j], non_blocking=True)        # device-to-device, ~3 us
+        self._stage_free[j].record(cur)
         res = self.step_device()
         if out_host is None:
             out_host = {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in ("scores", "clses", "bboxes", "affinity")}

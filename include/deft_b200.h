@@ -58,7 +58,8 @@ unsigned long long deft_launch_count(void);
  * small-M layers simply run unsplit). */
 int deft_tc_tile_n(int ldw, int M, int kind);
 size_t deft_tc_blob_bytes(int ldw, int K, int bn);
-int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, float* blob, deft_stream_t s);
+int deft_tc_pack_weights(const float* w_packed, int ldw, int K, int bn, int taps /* KH*KW of the conv that will use it (1 for a plain GEMM) */,
+                         float* blob, deft_stream_t s);
 size_t deft_tc_scratch_bytes(int ldw, int K, int M, int kind);
 
 /* ---- layout converters at the reference's NCHW boundary ------------------------------------ */
@@ -139,10 +140,13 @@ int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* ce
 /* ---- a7: AFE_module.forward_feature_extracter (AFE.py:88-92,162-188), evaluated sparsely: the
  * selector conv3x3+ReLU is computed only at the (up to) 4 bilinear corners of every centre.
  * maps_host[k] NHWC [1,H_k,W_k,C_k]; selw_host[k] packed [9*C_k][Co_k]; selb_host[k] [Co_k];
- * centres [N,2] (x,y) in [-1,1] (grid_sample, padding_mode=border); emb [N, sum Co_k]. */
+ * centres [N,2] (x,y) in [-1,1] (grid_sample, padding_mode=border); emb [N, sum Co_k].
+ * ws: >= deft_afe_extract_workspace_bytes(N) (per-corner partial sums). */
+size_t deft_afe_extract_workspace_bytes(int N);
 int deft_afe_extract(const float* const* maps_host, const int* pitch_host, const int* C_host, const int* H_host,
                      const int* W_host, const float* const* selw_host, const float* const* selb_host,
-                     const int* Co_host, const float* centres, int N, float* emb, int align_corners, deft_stream_t s);
+                     const int* Co_host, const float* centres, int N, float* emb, int align_corners,
+                     void* ws, size_t ws_bytes, deft_stream_t s);
 
 /* ---- a8: AFE_module.forward_stacker_features (AFE.py:110-160) for F memory frames in one call.
  * xp [F,P,Cemb] (rows >= n_f ignored), n_host[F]; xn [P,Cemb] (m live rows).
