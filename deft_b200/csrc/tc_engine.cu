@@ -21,8 +21,9 @@ namespace deft {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // one 128-byte swizzle row of fp32
-constexpr int TC_PRODUCERS = 256;
-constexpr int TC_THREADS = 320;                 // 8 producer/epilogue warps + MMA warp + TMEM/B warp
+constexpr int TC_PWARPS = 16;                   // A-producer / epilogue warps
+constexpr int TC_PRODUCERS = TC_PWARPS * 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA warp + TMEM/weight-copy warp
 constexpr int TC_A_TILE = TC_BM * 128;          // bytes
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_NUM_SMS = 148;
@@ -122,23 +123,85 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 
 // ------------------------------------------------------------------------------------------------ A producers
-// Thread t (0..255) owns 16-byte chunk c = t & 7 of rows r_i = (t >> 3) + 32 i, i = 0..3, of every k-block.
-// issue(kb, raw): start the global loads of k-block kb into registers; combine(kb, raw, v): turn them into
-// the 4 A-tile chunks.  DEPTH = how many k-blocks of loads are kept in flight.
+// Thread t (0..511) owns 16-byte chunk c = t & 7 of rows r_i = (t >> 3) + 64 i, i = 0..1, of every k-block.
+// The mainloop calls issue() once per k-block in ascending order (global loads into registers, DEPTH k-blocks in
+// flight) and combine() once per k-block in the same order, so producers keep incremental (tap, channel-block)
+// counters instead of dividing -- the producer path is instruction-issue bound, every instruction counts.
+constexpr int TC_ROWS = 2;
+
+// Fast path: one NHWC source, channel count a multiple of 32, K order = (32-channel block, tap, channel)
+// (tc_k_perm_taps) or a 1x1 conv / plain GEMM.  Per k-block: one LDS (tap offset), TC_ROWS predicated LDG.128.
+struct TcConvFastAP {
+    const float* src;
+    int pitch, H, W, OH, OW, KW, stride, pad, taps;
+    static constexpr int kExtraSmemBytes = 64;          // tap offset table (<= 9 taps used; 7x7 never comes here)
+    static constexpr int RAW = TC_ROWS;
+    static constexpr int DEPTH = 3;
+    const float* rowp_[TC_ROWS];
+    unsigned vmask_[TC_ROWS];
+    const int* toff_;
+    int tap_, cboff_;
+    __device__ __forceinline__ void init(int m0, int M, unsigned char* extra, int kb0) {
+        int* toff = reinterpret_cast<int*>(extra);
+        if (threadIdx.x < taps) {
+            int ky = threadIdx.x / KW, kx = threadIdx.x - ky * KW;
+            toff[threadIdx.x] = ((ky - pad) * W + (kx - pad)) * pitch;
+        }
+        toff_ = toff;
+#pragma unroll
+        for (int i = 0; i < TC_ROWS; ++i) {
+            const int p = m0 + (threadIdx.x >> 3) + 64 * i;
+            vmask_[i] = 0;
+            rowp_[i] = src;
+            if (p < M) {
+                const int n = p / (OH * OW);
+                const int r = p - n * (OH * OW);
+                const int oy = (r / OW) * stride, ox = (r - (r / OW) * OW) * stride;
+                rowp_[i] = src + (((size_t)n * H + oy) * W + ox) * pitch + (threadIdx.x & 7) * 4;
+                for (int t = 0; t < taps; ++t) {
+                    const int iy = oy - pad + t / KW, ix = ox - pad + t % KW;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) vmask_[i] |= 1u << t;
+                }
+            }
+        }
+        const int cb = kb0 / taps;
+        tap_ = kb0 - cb * taps;
+        cboff_ = cb * TC_BK;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
+        const int off = toff_[tap_] + cboff_;
+#pragma unroll
+        for (int i = 0; i < TC_ROWS; ++i) {
+            raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((vmask_[i] >> tap_) & 1u) raw[i] = ldg4(rowp_[i] + off);
+        }
+        if (++tap_ == taps) { tap_ = 0; cboff_ += TC_BK; }
+    }
+    __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[TC_ROWS]) {
+#pragma unroll
+        for (int i = 0; i < TC_ROWS; ++i) v[i] = raw[i];
+    }
+};
+
+// General path: channel concat of up to 4 sources and/or channel counts that are not multiples of 32
+// (Root 1x1 convs, the 16-channel full-resolution layers).  K order as tc_k_perm_taps says.
 struct TcConvAP {
     ConvAP a;
     int K;
     int perm_taps;       // 0 = tap-major K order, else KH*KW with channel-block-major order (tc_k_perm_taps)
     static constexpr int kExtraSmemBytes = 0;
-    static constexpr int RAW = 4;
+    static constexpr int RAW = TC_ROWS;
     static constexpr int DEPTH = 2;
-    int n_[4], oy_[4], ox_[4];
+    int n_[TC_ROWS], oy_[TC_ROWS], ox_[TC_ROWS];
     unsigned valid_;
-    __device__ __forceinline__ void init(int m0, int M, unsigned char*) {
+    int kb_;
+    __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
         valid_ = 0;
+        kb_ = kb0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int p = m0 + (threadIdx.x >> 3) + 32 * i;
+        for (int i = 0; i < TC_ROWS; ++i) {
+            int p = m0 + (threadIdx.x >> 3) + 64 * i;
             bool v = p < M;
             if (v) valid_ |= 1u << i;
             int q = v ? p : 0;
@@ -148,14 +211,15 @@ struct TcConvAP {
             ox_[i] = (r - (r / a.OW) * a.OW) * a.stride - a.pad;
         }
     }
-    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
+    __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
+        const int kb = kb_++;
         int tap, cc;
         bool kok = true;
-        if (perm_taps) {          // K order = (32-channel block, tap, channel): the 9 taps of a block hit L1
+        if (perm_taps) {
             const int cb = kb / perm_taps;
             tap = kb - cb * perm_taps;
             cc = cb * TC_BK + (threadIdx.x & 7) * 4;
-        } else {                  // K order = (tap, channel)
+        } else {
             const int k = kb * TC_BK + (threadIdx.x & 7) * 4;
             tap = k / a.Ctot;
             cc = k - tap * a.Ctot;
@@ -167,7 +231,7 @@ struct TcConvAP {
         const float* base = a.src[s];
         const int pitch = a.pitch[s];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TC_ROWS; ++i) {
             int iy = oy_[i] + ky;
             int ix = ox_[i] + kx;
             raw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -175,21 +239,26 @@ struct TcConvAP {
                 raw[i] = ldg4(base + (((size_t)n_[i] * a.H + iy) * a.W + ix) * pitch + cc);
         }
     }
-    __device__ __forceinline__ void combine(int, const float4 (&raw)[RAW], float4 (&v)[4]) const {
+    __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[TC_ROWS]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = raw[i];
+        for (int i = 0; i < TC_ROWS; ++i) v[i] = raw[i];
     }
 };
 
+// DCNv2: A[p, k] = mask_tap(p) * bilinear(x[:, c]; p + tap + offset_tap(p)); K order = (32-channel block, tap, channel)
+// so that the 9 taps of a channel block re-read the same neighbourhood out of L1.  The 4 corner offsets/weights of
+// the tile's 128 pixels x 9 taps are computed once into smem.
 struct TcDcnAP {
     DcnAP a;
     int K;
     static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
-    static constexpr int RAW = 16;
-    static constexpr int DEPTH = 1;
+    static constexpr int RAW = TC_ROWS * 4;
+    static constexpr int DEPTH = 2;
     int4* tabO_;
     float4* tabW_;
-    __device__ __forceinline__ void init(int m0, int M, unsigned char* extra) {
+    const float* xc_;
+    int tap_i_, cboff_, tap_c_;
+    __device__ __forceinline__ void init(int m0, int M, unsigned char* extra, int kb0) {
         tabO_ = reinterpret_cast<int4*>(extra);
         tabW_ = reinterpret_cast<float4*>(extra + TC_BM * 9 * 16);
         const int H = a.H, W = a.W;
@@ -214,39 +283,37 @@ struct TcDcnAP {
                     float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
                     int base = n * H * W;
                     bool y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1;
-                    if (y0ok && x0ok) { o.x = base + y0 * W + x0; w.x = hy * hx * mk; }
-                    if (y0ok && x1ok) { o.y = base + y0 * W + x0 + 1; w.y = hy * lx * mk; }
-                    if (y1ok && x0ok) { o.z = base + (y0 + 1) * W + x0; w.z = ly * hx * mk; }
-                    if (y1ok && x1ok) { o.w = base + (y0 + 1) * W + x0 + 1; w.w = ly * lx * mk; }
+                    if (y0ok && x0ok) { o.x = (base + y0 * W + x0) * a.pitch; w.x = hy * hx * mk; }
+                    if (y0ok && x1ok) { o.y = (base + y0 * W + x0 + 1) * a.pitch; w.y = hy * lx * mk; }
+                    if (y1ok && x0ok) { o.z = (base + (y0 + 1) * W + x0) * a.pitch; w.z = ly * hx * mk; }
+                    if (y1ok && x1ok) { o.w = (base + (y0 + 1) * W + x0 + 1) * a.pitch; w.w = ly * lx * mk; }
                 }
             }
-            tabO_[idx] = o;       // corners with zero weight point at pixel 0: always a valid address
+            tabO_[idx] = o;       // element offsets; corners with zero weight point at element 0: always a valid address
             tabW_[idx] = w;
         }
-        // producers-only barrier (named barrier 1, 256 threads): the table is private to them
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int cb = kb0 / 9;
+        tap_i_ = tap_c_ = kb0 - cb * 9;
+        cboff_ = cb * TC_BK;
+        xc_ = a.x + (threadIdx.x & 7) * 4;
+        asm volatile("bar.sync 1, 512;" ::: "memory");     // producers only: the table is private to them
     }
-    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
-        // K order = (32-channel block, tap, channel): 9 consecutive k-blocks re-read the same neighbourhood -> L1 hits
-        const int cb = kb / 9;
-        const int tap = kb - cb * 9;
-        const int cc = cb * TC_BK + (threadIdx.x & 7) * 4;
-        const float* x = a.x + cc;
-        const int pitch = a.pitch;
+    __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
+        const float* x = xc_ + cboff_;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int4 o = tabO_[((threadIdx.x >> 3) + 32 * i) * 9 + tap];
-            raw[i * 4 + 0] = ldg4(x + (size_t)o.x * pitch);
-            raw[i * 4 + 1] = ldg4(x + (size_t)o.y * pitch);
-            raw[i * 4 + 2] = ldg4(x + (size_t)o.z * pitch);
-            raw[i * 4 + 3] = ldg4(x + (size_t)o.w * pitch);
+        for (int i = 0; i < TC_ROWS; ++i) {
+            const int4 o = tabO_[((threadIdx.x >> 3) + 64 * i) * 9 + tap_i_];
+            raw[i * 4 + 0] = ldg4(x + o.x);
+            raw[i * 4 + 1] = ldg4(x + o.y);
+            raw[i * 4 + 2] = ldg4(x + o.z);
+            raw[i * 4 + 3] = ldg4(x + o.w);
         }
+        if (++tap_i_ == 9) { tap_i_ = 0; cboff_ += TC_BK; }
     }
-    __device__ __forceinline__ void combine(int kb, const float4 (&raw)[RAW], float4 (&v)[4]) const {
-        const int tap = kb % 9;
+    __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[TC_ROWS]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 w = tabW_[((threadIdx.x >> 3) + 32 * i) * 9 + tap];
+        for (int i = 0; i < TC_ROWS; ++i) {
+            const float4 w = tabW_[((threadIdx.x >> 3) + 64 * i) * 9 + tap_c_];
             float4 acc;
             acc.x = w.x * raw[i * 4].x; acc.y = w.x * raw[i * 4].y; acc.z = w.x * raw[i * 4].z; acc.w = w.x * raw[i * 4].w;
             acc.x += w.y * raw[i * 4 + 1].x; acc.y += w.y * raw[i * 4 + 1].y; acc.z += w.y * raw[i * 4 + 1].z; acc.w += w.y * raw[i * 4 + 1].w;
@@ -254,6 +321,7 @@ struct TcDcnAP {
             acc.x += w.w * raw[i * 4 + 3].x; acc.y += w.w * raw[i * 4 + 3].y; acc.z += w.w * raw[i * 4 + 3].z; acc.w += w.w * raw[i * 4 + 3].w;
             v[i] = acc;
         }
+        if (++tap_c_ == 9) tap_c_ = 0;
     }
 };
 
@@ -262,14 +330,16 @@ struct TcPairAP {
     PairAP a;
     int K;
     static constexpr int kExtraSmemBytes = 0;
-    static constexpr int RAW = 8;
+    static constexpr int RAW = TC_ROWS * 2;
     static constexpr int DEPTH = 2;
-    const float* pa_[4];
-    const float* pb_[4];
-    __device__ __forceinline__ void init(int m0, int M, unsigned char*) {
+    const float* pa_[TC_ROWS];
+    const float* pb_[TC_ROWS];
+    int k_;
+    __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
+        k_ = kb0 * TC_BK + (threadIdx.x & 7) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int p = m0 + (threadIdx.x >> 3) + 32 * i;
+        for (int i = 0; i < TC_ROWS; ++i) {
+            int p = m0 + (threadIdx.x >> 3) + 64 * i;
             pa_[i] = nullptr;
             pb_[i] = nullptr;
             if (p < M) {
@@ -282,21 +352,21 @@ struct TcPairAP {
             }
         }
     }
-    __device__ __forceinline__ void issue(int kb, float4 (&raw)[RAW]) const {
-        const int k = kb * TC_BK + (threadIdx.x & 7) * 4;
+    __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TC_ROWS; ++i) {
             raw[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
             raw[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pa_[i] != nullptr && k < K) {
-                raw[2 * i] = ldg4(pa_[i] + k);
-                raw[2 * i + 1] = ldg4(pb_[i] + k);
+            if (pa_[i] != nullptr && k_ < K) {
+                raw[2 * i] = ldg4(pa_[i] + k_);
+                raw[2 * i + 1] = ldg4(pb_[i] + k_);
             }
         }
+        k_ += TC_BK;
     }
-    __device__ __forceinline__ void combine(int, const float4 (&raw)[RAW], float4 (&v)[4]) const {
+    __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[TC_ROWS]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TC_ROWS; ++i) {
             v[i].x = fmaxf(raw[2 * i].x + raw[2 * i + 1].x, 0.f); v[i].y = fmaxf(raw[2 * i].y + raw[2 * i + 1].y, 0.f);
             v[i].z = fmaxf(raw[2 * i].z + raw[2 * i + 1].z, 0.f); v[i].w = fmaxf(raw[2 * i].w + raw[2 * i + 1].w, 0.f);
         }
@@ -304,8 +374,37 @@ struct TcPairAP {
 };
 
 // ------------------------------------------------------------------------------------------------ epilogues
-// Interface: kSmemBytes; setup(smem, tid) by the 256 producer threads before the mainloop;
-// run<BN>(tmem_base, smem, warp, lane, m0, M, ntile) by warps 0-7 once the accumulator is complete.
+// 16 epilogue warps: TMEM lane quadrant = warp & 3, column group = warp >> 2.  A warp reads LW columns of its 32
+// rows per tcgen05.ld (one wait per LW columns, not per 8).
+template <int LW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[LW]) {
+    static_assert(LW == 8 || LW == 16 || LW == 32, "tmem_ld width");
+    uint32_t r[LW];
+    if constexpr (LW == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr) : "memory");
+    } else if constexpr (LW == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr) : "memory");
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+                     "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                       "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                       "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr) : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < LW; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Interface: kSmemBytes; setup(smem, tid) by the 512 producer threads before the mainloop;
+// run<BN>(tmem_base, smem, warp, lane, m0, M, ntile) by warps 0-15 once the accumulator is complete.
 struct EpiStd {
     Epilogue e;
     float* partial;      // split-K scratch [splits][M][ldp] or nullptr
@@ -314,38 +413,43 @@ struct EpiStd {
     __device__ __forceinline__ void setup(unsigned char*, int) const {}
     template <int BN>
     __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char*, int warp, int lane, int m0, int M, int ntile) const {
+        constexpr int NG = (BN / 8) < 4 ? (BN / 8) : 4;       // column groups
+        constexpr int CPG = BN / NG;                          // columns per group
+        constexpr int LW = CPG >= 32 ? 32 : CPG;              // columns per tcgen05.ld
+        const int g = warp >> 2;
+        if (g >= NG) return;
         const int lane_base = (warp & 3) * 32;
         const int p = m0 + lane_base + lane;
-        constexpr int COLS_PER_HALF = BN / 2;     // warps 0-3: first half of the columns, warps 4-7: second half
-        const int col0 = (warp >> 2) * COLS_PER_HALF;
 #pragma unroll 1
-        for (int c = 0; c < COLS_PER_HALF; c += 8) {
-            float v[8];
-            tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + c), v);
-            const int co = ntile * BN + col0 + c;
+        for (int c = 0; c < CPG; c += LW) {
+            float v[LW];
+            const int col = g * CPG + c;
+            tmem_ld<LW>(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
+            const int co = ntile * BN + col;
             if (p >= M) continue;
             if (partial != nullptr) {
                 float* dst = partial + ((size_t)blockIdx.z * M + p) * ldp + co;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int q = 0; q < LW / 4; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                 continue;
             }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < LW / 4; ++q) {
                 const int cq = co + q * 4;
-                if (cq >= e.Cout) break;
-                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e.scale) sc = ldg4(e.scale + cq);
-                if (e.shift) sh = ldg4(e.shift + cq);
-                float4 o;
-                o.x = v[q * 4 + 0] * sc.x + sh.x; o.y = v[q * 4 + 1] * sc.y + sh.y;
-                o.z = v[q * 4 + 2] * sc.z + sh.z; o.w = v[q * 4 + 3] * sc.w + sh.w;
-                if (e.residual) {
-                    float4 rr = ldg4(e.residual + (size_t)p * e.res_pitch + cq);
-                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                if (cq < e.Cout) {
+                    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e.scale) sc = ldg4(e.scale + cq);
+                    if (e.shift) sh = ldg4(e.shift + cq);
+                    float4 o;
+                    o.x = v[q * 4 + 0] * sc.x + sh.x; o.y = v[q * 4 + 1] * sc.y + sh.y;
+                    o.z = v[q * 4 + 2] * sc.z + sh.z; o.w = v[q * 4 + 3] * sc.w + sh.w;
+                    if (e.residual) {
+                        float4 rr = ldg4(e.residual + (size_t)p * e.res_pitch + cq);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(e.out + (size_t)p * e.out_pitch + cq) = o;
                 }
-                if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4*>(e.out + (size_t)p * e.out_pitch + cq) = o;
             }
         }
     }
@@ -369,47 +473,54 @@ struct EpiHeads {
         const int h = blockIdx.y;
         const int ch = c[h];
         for (int i = tid; i < ch * 256; i += TC_PRODUCERS) w2s[i] = w2[(size_t)row0[h] * 256 + i];
-        b1s[tid] = b1[h * 256 + tid];
-        // visibility to all epilogue warps is guaranteed by the producers' later named barrier in run()
+        if (tid < 256) b1s[tid] = b1[h * 256 + tid];
+        // visibility to all epilogue warps is guaranteed by the producers' named barrier in run()
     }
     template <int BN>
     __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char* smem, int warp, int lane, int m0, int M, int ntile) const {
         static_assert(BN == 256, "EpiHeads needs one 256-wide tile per head");
         const float* w2s = reinterpret_cast<const float*>(smem);
         const float* b1s = w2s + HEADS_MAXC * 256;
-        float* part = const_cast<float*>(b1s) + 256;          // [HEADS_MAXC][128] partials of the upper column half
+        float* part = const_cast<float*>(b1s) + 256;          // [HEADS_MAXC][128] running partials of column groups 1..3
         const int h = ntile;
         const int ch = c[h];
+        const int g = warp >> 2;                              // column group: 64 columns each
         const int lane_base = (warp & 3) * 32;
         const int row = lane_base + lane;
         const int p = m0 + row;
-        const int col0 = (warp >> 2) * 128;
         float acc[HEADS_MAXC];
 #pragma unroll
         for (int j = 0; j < HEADS_MAXC; ++j) acc[j] = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");        // w2s / b1s written by setup() are visible
+        asm volatile("bar.sync 1, 512;" ::: "memory");        // w2s / b1s written by setup() are visible
 #pragma unroll 1
-        for (int cb = 0; cb < 128; cb += 8) {
-            float v[8];
-            tmem_ld8(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)(col0 + cb), v);
+        for (int cb = 0; cb < 64; cb += 16) {
+            float v[16];
+            const int col = g * 64 + cb;
+            tmem_ld<16>(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + b1s[col0 + cb + j], 0.f);
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b1s[col + j], 0.f);
 #pragma unroll
             for (int o = 0; o < HEADS_MAXC; ++o) {
                 if (o < ch) {
-                    const float4 wa = *reinterpret_cast<const float4*>(w2s + o * 256 + col0 + cb);
-                    const float4 wb = *reinterpret_cast<const float4*>(w2s + o * 256 + col0 + cb + 4);
-                    acc[o] += v[0] * wa.x + v[1] * wa.y + v[2] * wa.z + v[3] * wa.w + v[4] * wb.x + v[5] * wb.y + v[6] * wb.z + v[7] * wb.w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w = *reinterpret_cast<const float4*>(w2s + o * 256 + col + q * 4);
+                        acc[o] += v[q * 4] * w.x + v[q * 4 + 1] * w.y + v[q * 4 + 2] * w.z + v[q * 4 + 3] * w.w;
+                    }
                 }
             }
         }
-        if (warp >= 4) {
+        // deterministic reduction over the 4 column groups through one [C_h][128] buffer: g=1 writes, g=2,3 add, g=0 reads
+#pragma unroll 1
+        for (int round = 1; round <= 3; ++round) {
+            if (g == round) {
 #pragma unroll
-            for (int o = 0; o < HEADS_MAXC; ++o)
-                if (o < ch) part[o * TC_BM + row] = acc[o];
+                for (int o = 0; o < HEADS_MAXC; ++o)
+                    if (o < ch) part[o * TC_BM + row] = (round == 1 ? 0.f : part[o * TC_BM + row]) + acc[o];
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (warp < 4 && p < M) {
+        if (g == 0 && p < M) {
             const int n = p / HW, q = p - n * HW;
 #pragma unroll
             for (int o = 0; o < HEADS_MAXC; ++o)
@@ -458,49 +569,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
         fence_mbar_init();
         fence_proxy_async();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == TC_PWARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)stages * STAGE_BYTES + 8 * 25);
 
-    if (warp < 8) {
+    if (warp < TC_PWARPS) {
         // ===================== A producers =====================
-        ap.init(m0, M, ap_extra);
+        ap.init(m0, M, ap_extra, kb0);
         epi.setup(epi_extra, tid);
-        const int chunk = tid & 7;
-        const int row0 = tid >> 3;
+        uint32_t soff[TC_ROWS];
+#pragma unroll
+        for (int r = 0; r < TC_ROWS; ++r) soff[r] = swz((tid >> 3) + 64 * r, tid & 7);
         float4 raw[AP::DEPTH][AP::RAW];
 #pragma unroll
         for (int d = 0; d < AP::DEPTH; ++d)
-            if (d < nkb) ap.issue(kb0 + d, raw[d]);
+            if (d < nkb) ap.issue(raw[d]);
+        int s = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < nkb; it += AP::DEPTH) {
 #pragma unroll
             for (int d = 0; d < AP::DEPTH; ++d) {
                 const int i = it + d;                     // local k-block index
                 if (i < nkb) {
-                    float4 v[4];
-                    ap.combine(kb0 + i, raw[d], v);
-                    if (i + AP::DEPTH < nkb) ap.issue(kb0 + i + AP::DEPTH, raw[d]);
-                    const int s = i % stages;
-                    const uint32_t ph = (uint32_t)(i / stages) & 1u;
+                    float4 v[TC_ROWS];
+                    ap.combine(raw[d], v);
+                    if (i + AP::DEPTH < nkb) ap.issue(raw[d]);
                     mbar_wait(empty(s), ph ^ 1u);
                     unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
-                    unsigned char* a_lo = a_hi + TC_A_TILE;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const uint32_t off = swz(row0 + 32 * r, chunk);
+                    for (int r = 0; r < TC_ROWS; ++r) {
                         float4 h;
                         h.x = tf32_rna(v[r].x); h.y = tf32_rna(v[r].y); h.z = tf32_rna(v[r].z); h.w = tf32_rna(v[r].w);
-                        *reinterpret_cast<float4*>(a_hi + off) = h;
+                        *reinterpret_cast<float4*>(a_hi + soff[r]) = h;
                         if (NPASS == 3) {
                             float4 l;
                             l.x = v[r].x - h.x; l.y = v[r].y - h.y; l.z = v[r].z - h.z; l.w = v[r].w - h.w;
-                            *reinterpret_cast<float4*>(a_lo + off) = l;
+                            *reinterpret_cast<float4*>(a_hi + TC_A_TILE + soff[r]) = l;
                         }
                     }
                     fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
                     mbar_arrive(full_a(s));
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -509,13 +620,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
         tc_fence_after();
         epi.template run<BN>(tmem_base, epi_extra, warp, lane, m0, M, ntile);
         tc_fence_before();
-    } else if (warp == 8) {
+    } else if (warp == TC_PWARPS) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % stages;
-                const uint32_t ph = (uint32_t)(i / stages) & 1u;
                 mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 tc_fence_after();
@@ -537,6 +648,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                     }
                 }
                 umma_commit(empty(s));            // slot free once these MMAs have read it
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
             umma_commit(accum_bar);               // accumulator complete
         }
@@ -546,19 +658,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
         if (lane == 0) {
             constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * nkb_total + kb0) * (2 * B_TILE);
+            int s = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % stages;
-                const uint32_t ph = (uint32_t)(i / stages) & 1u;
                 mbar_wait(empty(s), ph ^ 1u);
                 const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
                 mbar_arrive_expect_tx(full_b(s), bytes);
                 bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == 9) {
+    if (warp == TC_PWARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -714,10 +827,21 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     return DEFT_OK;
 }
 
+static TcConvFastAP make_fast_ap(const ConvAP& ap) {
+    TcConvFastAP f{};
+    f.src = ap.src[0]; f.pitch = ap.pitch[0]; f.H = ap.H; f.W = ap.W; f.OH = ap.OH; f.OW = ap.OW;
+    f.KW = ap.KW; f.stride = ap.stride; f.pad = ap.pad; f.taps = ap.KH * ap.KW;
+    return f;
+}
+
 int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                      size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
         if (ap.c[i] % 4 != 0) return DEFT_EINVAL;
+    if (ap.nsrc == 1 && ap.Ctot % TC_BK == 0 && ap.KH * ap.KW <= 9) {
+        // fast path: single source, channel-block-major K (what tc_k_perm_taps prescribes for Ctot % 32 == 0) or 1x1
+        return tc_dispatch(make_fast_ap(ap), blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+    }
     TcConvAP t{};
     t.a = ap;
     t.K = K;
@@ -749,13 +873,11 @@ int tc_heads_dispatch(const ConvAP& ap, const float* blob, int K, int M, const H
         if (ha.c[h] > HEADS_MAXC) return DEFT_EINVAL;
         epi.out[h] = ha.out[h]; epi.c[h] = ha.c[h]; epi.row0[h] = ha.row0[h];
     }
-    TcConvAP t{};
-    t.a = ap;
-    t.K = K;
-    t.perm_taps = tc_k_perm_taps(K, ap.KH * ap.KW);
+    if (ap.nsrc != 1 || ap.Ctot % TC_BK != 0 || ap.KH * ap.KW > 9) return DEFT_EINVAL;
+    TcConvFastAP t = make_fast_ap(ap);
     const int nkb = ceil_div(K, TC_BK);
-    if (flags & DEFT_FLAG_TF32X1) return tc_launch<TcConvAP, 256, 1, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
-    return tc_launch<TcConvAP, 256, 3, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
+    if (flags & DEFT_FLAG_TF32X1) return tc_launch<TcConvFastAP, 256, 1, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
+    return tc_launch<TcConvFastAP, 256, 3, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);
 }
 
 int tc_pack_weights(const float* wp, int ldw, int K, int bn, int taps, float* blob, cudaStream_t st) {
