@@ -75,14 +75,20 @@ __global__ void __launch_bounds__(256) afe_corner_kernel(AfeArgs a, const float*
             for (int tap = 0; tap < 9; ++tap) {
                 const int ky = tap / 3, kx = tap - ky * 3;
                 const float* wr = wk + ((size_t)tap * C + cc0) * Co + o;
-                for (int c4 = 0; c4 < cw4; ++c4) {
-                    const float w0 = __ldg(wr + (size_t)(c4 * 4 + 0) * Co), w1 = __ldg(wr + (size_t)(c4 * 4 + 1) * Co);
-                    const float w2 = __ldg(wr + (size_t)(c4 * 4 + 2) * Co), w3 = __ldg(wr + (size_t)(c4 * 4 + 3) * Co);
+                // channel counts are multiples of 16: 4 channel quads per step, their 16 weight loads issued together
+                // (the loop is latency-bound on these L2 loads otherwise)
+                for (int c4 = 0; c4 < cw4; c4 += 4) {
+                    float w[16];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int d = rg * 2 + (r >> 2), cy = (r >> 1) & 1, cx = r & 1;
-                        const float4 pv = *reinterpret_cast<const float4*>(&patch[(d * 16 + (cy + ky) * 4 + (cx + kx)) * AFE_CCHUNK + c4 * 4]);
-                        acc[r] += pv.x * w0 + pv.y * w1 + pv.z * w2 + pv.w * w3;
+                    for (int j = 0; j < 16; ++j) w[j] = __ldg(wr + (size_t)(c4 * 4 + j) * Co);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            const int d = rg * 2 + (r >> 2), cy = (r >> 1) & 1, cx = r & 1;
+                            const float4 pv = *reinterpret_cast<const float4*>(&patch[(d * 16 + (cy + ky) * 4 + (cx + kx)) * AFE_CCHUNK + (c4 + u) * 4]);
+                            acc[r] += pv.x * w[u * 4] + pv.y * w[u * 4 + 1] + pv.z * w[u * 4 + 2] + pv.w * w[u * 4 + 3];
+                        }
                     }
                 }
             }

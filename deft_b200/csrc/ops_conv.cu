@@ -2,6 +2,7 @@
 // DCNv2, depthwise-deconv upsample+add, CenterNet heads, layout converters.
 #include "igemm_simt.cuh"
 #include "tc_engine.cuh"
+#include "conv_c16.cuh"
 
 namespace deft {
 
@@ -282,6 +283,14 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
     Epilogue ep{scale, shift, residual, res_pitch, out, out_pitch, Cout, (flags & DEFT_FLAG_RELU) ? 1 : 0};
     int M = N * ap.OH * ap.OW;
     int K = KH * KW * ap.Ctot;
+    // the two HBM-bound 16-channel full-resolution layers (DLA level0 / level1): direct fp32 kernel
+    if (nsrc == 1 && src_c[0] == 16 && KH == 3 && KW == 3 && pad == 1 && residual == nullptr && !(flags & DEFT_FLAG_NO_DIRECT)) {
+        const int relu = (flags & DEFT_FLAG_RELU) ? 1 : 0;
+        if (Cout == 16 && ldw == 16 && stride == 1)
+            return launch_conv3x3_c16<16, 1, 4>(srcs[0], src_pitch[0], N, H, W, ap.OH, ap.OW, w_packed, ldw, scale, shift, out, out_pitch, relu, to_stream(s));
+        if (Cout == 32 && ldw == 32 && stride == 2)
+            return launch_conv3x3_c16<32, 2, 2>(srcs[0], src_pitch[0], N, H, W, ap.OH, ap.OW, w_packed, ldw, scale, shift, out, out_pitch, relu, to_stream(s));
+    }
     if (flags & DEFT_FLAG_TENSORCORE) {
         int rc = tc_conv_dispatch(ap, w_tc, tc_bn, ldw, K, M, ep, flags, ws, ws_bytes, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;   // EINVAL from the TC engine = shape not covered -> SIMT

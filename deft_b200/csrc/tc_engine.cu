@@ -16,14 +16,18 @@
 //   issuer, warp 9 TMEM allocator + lane 0 weight-tile bulk copies.  mbarrier ring of S stages:
 //   full_a (256 producer arrivals), full_b (tx bytes), empty (tcgen05.commit).
 #include "tc_engine.cuh"
+#include <stdlib.h>
 
 namespace deft {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // one 128-byte swizzle row of fp32
-constexpr int TC_PWARPS = 16;                   // A-producer / epilogue warps
+constexpr int TC_PWARPS = 16;                   // A-producer warps
+constexpr int TC_EWARPS = 4;                    // epilogue warps (one per TMEM lane quadrant)
 constexpr int TC_PRODUCERS = TC_PWARPS * 32;
-constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA warp + TMEM/weight-copy warp
+constexpr int TC_MMA_WARP = TC_PWARPS + TC_EWARPS;
+constexpr int TC_AUX_WARP = TC_MMA_WARP + 1;    // TMEM allocator + weight-tile bulk copies
+constexpr int TC_THREADS = (TC_AUX_WARP + 1) * 32;
 constexpr int TC_A_TILE = TC_BM * 128;          // bytes
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_NUM_SMS = 148;
@@ -141,13 +145,17 @@ struct TcConvFastAP {
     unsigned vmask_[TC_ROWS];
     const int* toff_;
     int tap_, cboff_;
-    __device__ __forceinline__ void init(int m0, int M, unsigned char* extra, int kb0) {
+    __device__ __forceinline__ void setup_once(unsigned char* extra) {       // tile-independent: tap offset table
         int* toff = reinterpret_cast<int*>(extra);
         if (threadIdx.x < taps) {
             int ky = threadIdx.x / KW, kx = threadIdx.x - ky * KW;
             toff[threadIdx.x] = ((ky - pad) * W + (kx - pad)) * pitch;
         }
         toff_ = toff;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
+        const int KH = taps / KW;
 #pragma unroll
         for (int i = 0; i < TC_ROWS; ++i) {
             const int p = m0 + (threadIdx.x >> 3) + 64 * i;
@@ -158,16 +166,17 @@ struct TcConvFastAP {
                 const int r = p - n * (OH * OW);
                 const int oy = (r / OW) * stride, ox = (r - (r / OW) * OW) * stride;
                 rowp_[i] = src + (((size_t)n * H + oy) * W + ox) * pitch + (threadIdx.x & 7) * 4;
-                for (int t = 0; t < taps; ++t) {
-                    const int iy = oy - pad + t / KW, ix = ox - pad + t % KW;
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) vmask_[i] |= 1u << t;
-                }
+                unsigned bit = 1u;
+                for (int ky = 0; ky < KH; ++ky)
+                    for (int kx = 0; kx < KW; ++kx, bit <<= 1) {
+                        const int iy = oy - pad + ky, ix = ox - pad + kx;
+                        if (iy >= 0 && iy < H && ix >= 0 && ix < W) vmask_[i] |= bit;
+                    }
             }
         }
         const int cb = kb0 / taps;
         tap_ = kb0 - cb * taps;
         cboff_ = cb * TC_BK;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
     }
     __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
         const int off = toff_[tap_] + cboff_;
@@ -196,6 +205,7 @@ struct TcConvAP {
     int n_[TC_ROWS], oy_[TC_ROWS], ox_[TC_ROWS];
     unsigned valid_;
     int kb_;
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
         valid_ = 0;
         kb_ = kb0;
@@ -253,15 +263,17 @@ struct TcDcnAP {
     int K;
     static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
     static constexpr int RAW = TC_ROWS * 4;
-    static constexpr int DEPTH = 2;
+    static constexpr int DEPTH = 1;      // 8 float4 in flight per thread; a second set would spill under the 80-register cap
     int4* tabO_;
     float4* tabW_;
     const float* xc_;
     int tap_i_, cboff_, tap_c_;
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void init(int m0, int M, unsigned char* extra, int kb0) {
         tabO_ = reinterpret_cast<int4*>(extra);
         tabW_ = reinterpret_cast<float4*>(extra + TC_BM * 9 * 16);
         const int H = a.H, W = a.W;
+        asm volatile("bar.sync 1, 512;" ::: "memory");     // every producer is done reading the previous tile's table
         for (int idx = threadIdx.x; idx < TC_BM * 9; idx += TC_PRODUCERS) {
             int row = idx / 9, tap = idx - row * 9;
             int p = m0 + row;
@@ -335,6 +347,7 @@ struct TcPairAP {
     const float* pa_[TC_ROWS];
     const float* pb_[TC_ROWS];
     int k_;
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
         k_ = kb0 * TC_BK + (threadIdx.x & 7) * 4;
 #pragma unroll
@@ -403,32 +416,26 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[LW]) {
     for (int i = 0; i < LW; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Interface: kSmemBytes; setup(smem, tid) by the 512 producer threads before the mainloop;
-// run<BN>(tmem_base, smem, warp, lane, m0, M, ntile) by warps 0-15 once the accumulator is complete.
+// Epilogue functors, run by the 4 dedicated epilogue warps (TMEM lane quadrant = warp & 3; a thread owns one
+// accumulator row): run<BN>(tmem_acc, smem, ewarp, lane, m0, M, ntile, z).
 struct EpiStd {
     Epilogue e;
     float* partial;      // split-K scratch [splits][M][ldp] or nullptr
     int ldp;
     static constexpr int kSmemBytes = 0;
-    __device__ __forceinline__ void setup(unsigned char*, int) const {}
     template <int BN>
-    __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char*, int warp, int lane, int m0, int M, int ntile) const {
-        constexpr int NG = (BN / 8) < 4 ? (BN / 8) : 4;       // column groups
-        constexpr int CPG = BN / NG;                          // columns per group
-        constexpr int LW = CPG >= 32 ? 32 : CPG;              // columns per tcgen05.ld
-        const int g = warp >> 2;
-        if (g >= NG) return;
-        const int lane_base = (warp & 3) * 32;
+    __device__ __forceinline__ void run(uint32_t tmem_acc, unsigned char*, int ewarp, int lane, int m0, int M, int ntile, int z) const {
+        constexpr int LW = BN >= 32 ? 32 : BN;                // columns per tcgen05.ld
+        const int lane_base = ewarp * 32;
         const int p = m0 + lane_base + lane;
 #pragma unroll 1
-        for (int c = 0; c < CPG; c += LW) {
+        for (int c = 0; c < BN; c += LW) {
             float v[LW];
-            const int col = g * CPG + c;
-            tmem_ld<LW>(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
-            const int co = ntile * BN + col;
+            tmem_ld<LW>(tmem_acc + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+            const int co = ntile * BN + c;
             if (p >= M) continue;
             if (partial != nullptr) {
-                float* dst = partial + ((size_t)blockIdx.z * M + p) * ldp + co;
+                float* dst = partial + ((size_t)z * M + p) * ldp + co;
 #pragma unroll
                 for (int q = 0; q < LW / 4; ++q) *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                 continue;
@@ -466,76 +473,66 @@ struct EpiHeads {
     int c[DEFT_MAX_HEADS];
     int row0[DEFT_MAX_HEADS];
     int HW;
-    static constexpr int kSmemBytes = HEADS_MAXC * 256 * 4 + 256 * 4 + HEADS_MAXC * TC_BM * 4;
-    __device__ __forceinline__ void setup(unsigned char* smem, int tid) const {
+    static constexpr int kSmemBytes = HEADS_MAXC * 256 * 4 + 256 * 4 + 16;
+    template <int BN>
+    __device__ __forceinline__ void run(uint32_t tmem_acc, unsigned char* smem, int ewarp, int lane, int m0, int M, int ntile, int) const {
+        static_assert(BN == 256, "EpiHeads needs one 256-wide tile per head");
         float* w2s = reinterpret_cast<float*>(smem);
         float* b1s = w2s + HEADS_MAXC * 256;
-        const int h = blockIdx.y;
-        const int ch = c[h];
-        for (int i = tid; i < ch * 256; i += TC_PRODUCERS) w2s[i] = w2[(size_t)row0[h] * 256 + i];
-        if (tid < 256) b1s[tid] = b1[h * 256 + tid];
-        // visibility to all epilogue warps is guaranteed by the producers' named barrier in run()
-    }
-    template <int BN>
-    __device__ __forceinline__ void run(uint32_t tmem_base, unsigned char* smem, int warp, int lane, int m0, int M, int ntile) const {
-        static_assert(BN == 256, "EpiHeads needs one 256-wide tile per head");
-        const float* w2s = reinterpret_cast<const float*>(smem);
-        const float* b1s = w2s + HEADS_MAXC * 256;
-        float* part = const_cast<float*>(b1s) + 256;          // [HEADS_MAXC][128] running partials of column groups 1..3
+        int* cur_head = reinterpret_cast<int*>(b1s + 256);
         const int h = ntile;
         const int ch = c[h];
-        const int g = warp >> 2;                              // column group: 64 columns each
-        const int lane_base = (warp & 3) * 32;
-        const int row = lane_base + lane;
-        const int p = m0 + row;
+        const int etid = ewarp * 32 + lane;
+        // (re)stage this head's 1x1 weights; named barrier 2 = the 128 epilogue threads
+        asm volatile("bar.sync 2, 128;" ::: "memory");        // previous tile's readers are done
+        for (int i = etid; i < ch * 256; i += TC_EWARPS * 32) w2s[i] = w2[(size_t)row0[h] * 256 + i];
+        for (int i = etid; i < 256; i += TC_EWARPS * 32) b1s[i] = b1[h * 256 + i];
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        (void)cur_head;
+        const int lane_base = ewarp * 32;
+        const int p = m0 + lane_base + lane;
         float acc[HEADS_MAXC];
 #pragma unroll
         for (int j = 0; j < HEADS_MAXC; ++j) acc[j] = 0.f;
-        asm volatile("bar.sync 1, 512;" ::: "memory");        // w2s / b1s written by setup() are visible
 #pragma unroll 1
-        for (int cb = 0; cb < 64; cb += 16) {
+        for (int cb = 0; cb < 256; cb += 16) {
             float v[16];
-            const int col = g * 64 + cb;
-            tmem_ld<16>(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)col, v);
+            tmem_ld<16>(tmem_acc + ((uint32_t)lane_base << 16) + (uint32_t)cb, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b1s[col + j], 0.f);
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + b1s[cb + j], 0.f);
 #pragma unroll
             for (int o = 0; o < HEADS_MAXC; ++o) {
                 if (o < ch) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 w = *reinterpret_cast<const float4*>(w2s + o * 256 + col + q * 4);
+                        const float4 w = *reinterpret_cast<const float4*>(w2s + o * 256 + cb + q * 4);
                         acc[o] += v[q * 4] * w.x + v[q * 4 + 1] * w.y + v[q * 4 + 2] * w.z + v[q * 4 + 3] * w.w;
                     }
                 }
             }
         }
-        // deterministic reduction over the 4 column groups through one [C_h][128] buffer: g=1 writes, g=2,3 add, g=0 reads
-#pragma unroll 1
-        for (int round = 1; round <= 3; ++round) {
-            if (g == round) {
-#pragma unroll
-                for (int o = 0; o < HEADS_MAXC; ++o)
-                    if (o < ch) part[o * TC_BM + row] = (round == 1 ? 0.f : part[o * TC_BM + row]) + acc[o];
-            }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-        }
-        if (g == 0 && p < M) {
+        if (p < M) {
             const int n = p / HW, q = p - n * HW;
 #pragma unroll
             for (int o = 0; o < HEADS_MAXC; ++o)
-                if (o < ch) out[h][((size_t)n * ch + o) * HW + q] = acc[o] + part[o * TC_BM + row] + b2[row0[h] + o];
+                if (o < ch) out[h][((size_t)n * ch + o) * HW + q] = acc[o] + b2[row0[h] + o];
         }
     }
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
+// Persistent: gridDim.x CTAs (<= #SMs) walk the tile list t = blockIdx.x, +gridDim.x, ...; tile = (m_tile, n_tile,
+// k-split).  The smem ring and its phases run straight through tile boundaries; the accumulator is double-buffered
+// in TMEM so the epilogue warps drain tile i while the tensor core already works on tile i+1.
+struct TileSched {
+    int m_tiles, n_tiles, splits, total, nkb_total, kb_per_split;
+};
 template <class AP, int BN, int NPASS, class EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, int nkb_total, int kb_per_split,
-                                                                 int M, int stages, EPI epi) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, TileSched ts, int M, int stages, EPI epi,
+                                                                 int dbg) {
     constexpr int B_TILE = BN * 128;                      // bytes of one B part (hi or lo)
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms must sit on 1024 B boundaries)
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -547,131 +544,169 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     auto full_a = [&](int s) { return bar_base + 8u * s; };
     auto full_b = [&](int s) { return bar_base + 8u * (8 + s); };
     auto empty = [&](int s) { return bar_base + 8u * (16 + s); };
-    const uint32_t accum_bar = bar_base + 8u * 24;
-    const uint32_t tmem_slot = bar_base + 8u * 25;
+    auto acc_full = [&](int b) { return bar_base + 8u * (24 + b); };
+    auto acc_empty = [&](int b) { return bar_base + 8u * (26 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * 28;
     unsigned char* ap_extra = smem + (size_t)stages * STAGE_BYTES + 256;
     unsigned char* epi_extra = ap_extra + AP::kExtraSmemBytes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * TC_BM;
-    const int ntile = blockIdx.y;
-    const int kb0 = blockIdx.z * kb_per_split;
-    const int kb1 = min(nkb_total, kb0 + kb_per_split);
-    const int nkb = kb1 - kb0;                            // >= 1 by construction of the split
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full_a(s), TC_PRODUCERS);
+            mbar_init(full_a(s), TC_PWARPS);              // one arrival per producer warp
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), TC_EWARPS);
+        }
         fence_mbar_init();
         fence_proxy_async();
     }
-    if (warp == TC_PWARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == TC_AUX_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)stages * STAGE_BYTES + 8 * 25);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)stages * STAGE_BYTES + 8 * 28);
+    const int tiles_mn = ts.m_tiles * ts.n_tiles;
 
     if (warp < TC_PWARPS) {
         // ===================== A producers =====================
-        ap.init(m0, M, ap_extra, kb0);
-        epi.setup(epi_extra, tid);
+        ap.setup_once(ap_extra);
         uint32_t soff[TC_ROWS];
 #pragma unroll
         for (int r = 0; r < TC_ROWS; ++r) soff[r] = swz((tid >> 3) + 64 * r, tid & 7);
-        float4 raw[AP::DEPTH][AP::RAW];
-#pragma unroll
-        for (int d = 0; d < AP::DEPTH; ++d)
-            if (d < nkb) ap.issue(raw[d]);
         int s = 0;
         uint32_t ph = 0;
-        for (int it = 0; it < nkb; it += AP::DEPTH) {
+        // dbg bits (DEFT_TC_DBG, perf bring-up only): 1 no B copy, 2 no A global loads, 4 no A smem stores/fence, 8 no MMA, 16 no epilogue
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+            const int z = t / tiles_mn, mn = t - z * tiles_mn;
+            const int m0 = (mn / ts.n_tiles) * TC_BM;
+            const int kb0 = z * ts.kb_per_split;
+            const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
+            ap.init(m0, M, ap_extra, kb0);
+            float4 raw[AP::DEPTH][AP::RAW];
 #pragma unroll
-            for (int d = 0; d < AP::DEPTH; ++d) {
-                const int i = it + d;                     // local k-block index
-                if (i < nkb) {
-                    float4 v[TC_ROWS];
-                    ap.combine(raw[d], v);
-                    if (i + AP::DEPTH < nkb) ap.issue(raw[d]);
-                    mbar_wait(empty(s), ph ^ 1u);
-                    unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
+            for (int d = 0; d < AP::DEPTH; ++d)
+                if (d < nkb) ap.issue(raw[d]);
+            for (int it = 0; it < nkb; it += AP::DEPTH) {
 #pragma unroll
-                    for (int r = 0; r < TC_ROWS; ++r) {
-                        float4 h;
-                        h.x = tf32_rna(v[r].x); h.y = tf32_rna(v[r].y); h.z = tf32_rna(v[r].z); h.w = tf32_rna(v[r].w);
-                        *reinterpret_cast<float4*>(a_hi + soff[r]) = h;
-                        if (NPASS == 3) {
-                            float4 l;
-                            l.x = v[r].x - h.x; l.y = v[r].y - h.y; l.z = v[r].z - h.z; l.w = v[r].w - h.w;
-                            *reinterpret_cast<float4*>(a_hi + TC_A_TILE + soff[r]) = l;
+                for (int d = 0; d < AP::DEPTH; ++d) {
+                    const int i = it + d;                     // local k-block index
+                    if (i < nkb) {
+                        float4 v[TC_ROWS];
+                        ap.combine(raw[d], v);
+                        if (i + AP::DEPTH < nkb && !(dbg & 2)) ap.issue(raw[d]);
+                        mbar_wait(empty(s), ph ^ 1u);
+                        unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+                        for (int r = 0; r < TC_ROWS; ++r) {
+                            if (dbg & 4) break;
+                            float4 h;
+                            h.x = tf32_rna(v[r].x); h.y = tf32_rna(v[r].y); h.z = tf32_rna(v[r].z); h.w = tf32_rna(v[r].w);
+                            *reinterpret_cast<float4*>(a_hi + soff[r]) = h;
+                            if (NPASS == 3) {
+                                float4 l;
+                                l.x = v[r].x - h.x; l.y = v[r].y - h.y; l.z = v[r].z - h.z; l.w = v[r].w - h.w;
+                                *reinterpret_cast<float4*>(a_hi + TC_A_TILE + soff[r]) = l;
+                            }
                         }
+                        if (!(dbg & 4)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_a(s)); // one arrival per warp: 16 per stage, not 512
+                        if (++s == stages) { s = 0; ph ^= 1u; }
                     }
-                    fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
-                    mbar_arrive(full_a(s));
-                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
-        // ===================== epilogue =====================
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        epi.template run<BN>(tmem_base, epi_extra, warp, lane, m0, M, ntile);
-        tc_fence_before();
-    } else if (warp == TC_PWARPS) {
+    } else if (warp < TC_MMA_WARP) {
+        // ===================== epilogue warps =====================
+        const int ewarp = warp - TC_PWARPS;
+        int iter = 0;
+        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
+            const int z = t / tiles_mn, mn = t - z * tiles_mn;
+            const int m0 = (mn / ts.n_tiles) * TC_BM, ntile = mn % ts.n_tiles;
+            const int b = iter & 1;
+            mbar_wait(acc_full(b), (uint32_t)(iter >> 1) & 1u);
+            tc_fence_after();
+            if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * BN), epi_extra, ewarp, lane, m0, M, ntile, z);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(b));
+        }
+    } else if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
-            int s = 0;
+            int s = 0, iter = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
+                const int z = t / tiles_mn;
+                const int kb0 = z * ts.kb_per_split;
+                const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
+                const int b = iter & 1;
+                mbar_wait(acc_empty(b), ((uint32_t)(iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = sbase + (uint32_t)s * STAGE_BYTES;
-                const uint32_t a_lo = a_hi + TC_A_TILE;
-                const uint32_t b_hi = a_hi + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
-                const uint32_t b_lo = b_hi + B_TILE;
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(full_a(s), ph);
+                    mbar_wait(full_b(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = sbase + (uint32_t)s * STAGE_BYTES;
+                    const uint32_t a_lo = a_hi + TC_A_TILE;
+                    const uint32_t b_hi = a_hi + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
+                    const uint32_t b_lo = b_hi + B_TILE;
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
-                    if (NPASS == 3) {
-                        // small terms first, so the big hi*hi product is added to an already-formed correction
-                        const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
-                        umma_tf32(tmem_base, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-                        umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
-                    } else {
-                        umma_tf32(tmem_base, da_hi, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        if (dbg & 8) break;
+                        const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
+                        if (NPASS == 3) {
+                            // small terms first, so the big hi*hi product is added to an already-formed correction
+                            const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
+                            umma_tf32(tmem_acc, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32(tmem_acc, da_hi, db_lo, idesc, 1u);
+                            umma_tf32(tmem_acc, da_hi, db_hi, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_acc, da_hi, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
+                    umma_commit(empty(s));            // slot free once these MMAs have read it
+                    if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(empty(s));            // slot free once these MMAs have read it
-                if (++s == stages) { s = 0; ph ^= 1u; }
+                umma_commit(acc_full(b));             // accumulator complete
             }
-            umma_commit(accum_bar);               // accumulator complete
         }
         __syncwarp();
     } else {
         // ===================== weight-tile bulk copies (one thread) =====================
         if (lane == 0) {
             constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * nkb_total + kb0) * (2 * B_TILE);
             int s = 0;
             uint32_t ph = 0;
-            for (int i = 0; i < nkb; ++i) {
-                mbar_wait(empty(s), ph ^ 1u);
-                const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
-                mbar_arrive_expect_tx(full_b(s), bytes);
-                bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
-                if (++s == stages) { s = 0; ph ^= 1u; }
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int ntile = mn % ts.n_tiles;
+                const int kb0 = z * ts.kb_per_split;
+                const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * ts.nkb_total + kb0) * (2 * B_TILE);
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
+                    if (dbg & 1) { mbar_arrive(full_b(s)); }
+                    else {
+                        mbar_arrive_expect_tx(full_b(s), bytes);
+                        bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
+                    }
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    if (warp == TC_PWARPS + 1) {
+    if (warp == TC_AUX_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -774,12 +809,16 @@ static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
     constexpr int B_TILE = BN * 128;
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + AP::kExtraSmemBytes + EPI::kSmemBytes;
-    const int kb_per_split = ceil_div(nkb, splits);
-    splits = ceil_div(nkb, kb_per_split);                // no empty split
+    TileSched ts{};
+    ts.kb_per_split = ceil_div(nkb, splits);
+    ts.splits = ceil_div(nkb, ts.kb_per_split);          // no empty split
+    ts.m_tiles = ceil_div(M, TC_BM);
+    ts.n_tiles = n_tiles;
+    ts.nkb_total = nkb;
+    ts.total = ts.m_tiles * ts.n_tiles * ts.splits;
     int stages = (TC_SMEM_LIMIT - fixed) / STAGE_BYTES;
-    if (stages > 4) stages = 4;
-    if (stages > kb_per_split) stages = kb_per_split;
-    if (stages < 1 || (stages < 2 && kb_per_split > 1)) return DEFT_EINVAL;
+    if (stages > 6) stages = 6;
+    if (stages < 2) return DEFT_EINVAL;
     size_t smem = (size_t)stages * STAGE_BYTES + fixed;
     static bool attr_done = false;
     if (!attr_done) {
@@ -789,8 +828,11 @@ static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
         }
         attr_done = true;
     }
-    dim3 grid(ceil_div(M, TC_BM), n_tiles, splits);
-    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, nkb, kb_per_split, M, stages, epi);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("DEFT_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    if (const char* e = getenv("DEFT_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) { stages = v; } }
+    const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
+    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, stages, epi, dbg);
     DEFT_CHECK_LAUNCH("tc_igemm_kernel");
     return DEFT_OK;
 }

@@ -38,6 +38,7 @@ typedef void* deft_stream_t; /* cudaStream_t */
 #define DEFT_FLAG_RELU 1u
 #define DEFT_FLAG_TENSORCORE 2u   /* use the tcgen05 (3xTF32) engine where available */
 #define DEFT_FLAG_TF32X1 4u       /* single-pass TF32 (faster, ~1e-3 per layer)      */
+#define DEFT_FLAG_NO_DIRECT 8u    /* conv: skip the specialised direct kernels (testing the generic engines) */
 
 #define DEFT_MAX_SRC 4
 #define DEFT_MAX_HEADS 12

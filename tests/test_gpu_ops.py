@@ -68,6 +68,24 @@ def test_conv_bn_act(dev, cin, cout, k, stride, hw, flags):
     assert nerr(out.nchw_view().cpu(), ref) < tol_for(flags)
 
 
+@pytest.mark.parametrize("cout,stride,hw", [(16, 1, (37, 70)), (16, 1, (64, 128)), (32, 2, (38, 70)), (32, 2, (64, 96))])
+def test_conv_c16_direct_kernel(dev, cout, stride, hw):
+    """The specialised direct kernel for DLA level0 (16->16) / level1 (16->32, stride 2): no residual, odd sizes,
+    batch 2; also cross-checked against the generic fp32 engine (DEFT_FLAG_NO_DIRECT = 8)."""
+    from deft_b200 import ops, packing
+    sp = {"c.weight": ("conv", (cout, 16, 3, 3))}
+    spec._bn(sp, "b", cout)
+    sd = spec.make_state_dict(sp, seed=cout + stride)
+    x = rnd((2, 16, *hw), f"c16{cout}")
+    ref = F.relu(restate.bn_eval(sd, "b", F.conv2d(x, sd["c.weight"], stride=stride, padding=1)))
+    wp, ldw = packing.pack_conv(sd["c.weight"].to(dev))
+    sc, sh = packing.fold_bn({k_: v.to(dev) for k_, v in sd.items()}, "b")
+    out = ops.conv2d_bn_act([ops.as_nhwc(x.to(dev))], wp, ldw, sc, sh, cout, 3, 3, stride, 1, True)
+    gen = ops.conv2d_bn_act([ops.as_nhwc(x.to(dev))], wp, ldw, sc, sh, cout, 3, 3, stride, 1, True, flags=8)
+    assert nerr(out.nchw_view().cpu(), ref) < TOL_FP32
+    assert nerr(gen.nchw_view().cpu(), ref) < TOL_FP32
+
+
 @pytest.mark.parametrize("flags", ENGINES)
 def test_conv_concat_root(dev, flags):
     """Root: 1x1 conv over a channel concat of 4 sources (dla.py:199-207) without materialising the cat."""
