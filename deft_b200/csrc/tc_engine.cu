@@ -102,6 +102,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+// Warp-convergent leader election (CUTLASS elect_one_sync): tcgen05.mma / commit / bulk copies issued under this
+// predicate compile to plain uniform-datapath instructions; issued from a divergent `lane == 0` branch instead, every
+// UTCHMMA gets wrapped in an ELECT + BRA.U.ANY serialisation loop (~90 cycles per MMA, measured).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred)::"memory");
+    return pred;
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -529,7 +538,9 @@ struct TileSched {
 };
 template <class AP, int BN, int NPASS, class EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, TileSched ts, int M, int stages, EPI epi,
-                                                                 int dbg) {
+                                                                 int dbg, long long* trace) {
+    // trace (DEFT_TC_TRACE, perf bring-up only): CTA 0 records clock64() at protocol points, [role][k-block < 96][4]
+#define TC_TRACE(role, idx, slot) do { if (trace != nullptr && blockIdx.x == 0 && (idx) < 96) trace[((role) * 96 + (idx)) * 4 + (slot)] = clock64(); } while (0)
     constexpr int B_TILE = BN * 128;                      // bytes of one B part (hi or lo)
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
     constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
@@ -578,7 +589,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
         uint32_t soff[TC_ROWS];
 #pragma unroll
         for (int r = 0; r < TC_ROWS; ++r) soff[r] = swz((tid >> 3) + 64 * r, tid & 7);
-        int s = 0;
+        int s = 0, gk = 0;
         uint32_t ph = 0;
         // dbg bits (DEFT_TC_DBG, perf bring-up only): 1 no B copy, 2 no A global loads, 4 no A smem stores/fence, 8 no MMA, 16 no epilogue
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
@@ -597,9 +608,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                     const int i = it + d;                     // local k-block index
                     if (i < nkb) {
                         float4 v[TC_ROWS];
+                        if (tid == 0) TC_TRACE(1, gk, 0);
                         ap.combine(raw[d], v);
                         if (i + AP::DEPTH < nkb && !(dbg & 2)) ap.issue(raw[d]);
+                        if (tid == 0) TC_TRACE(1, gk, 1);
                         mbar_wait(empty(s), ph ^ 1u);
+                        if (tid == 0) TC_TRACE(1, gk, 2);
                         unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
 #pragma unroll
                         for (int r = 0; r < TC_ROWS; ++r) {
@@ -616,6 +630,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                         if (!(dbg & 4)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_a(s)); // one arrival per warp: 16 per stage, not 512
+                        if (tid == 0) TC_TRACE(1, gk, 3);
+                        ++gk;
                         if (++s == stages) { s = 0; ph ^= 1u; }
                     }
                 }
@@ -629,18 +645,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
             const int m0 = (mn / ts.n_tiles) * TC_BM, ntile = mn % ts.n_tiles;
             const int b = iter & 1;
+            if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 0);
             mbar_wait(acc_full(b), (uint32_t)(iter >> 1) & 1u);
+            if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
             if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * BN), epi_extra, ewarp, lane, m0, M, ntile, z);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(b));
+            if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 2);
         }
     } else if (warp == TC_MMA_WARP) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = make_idesc(BN);
-            int s = 0, iter = 0;
+            int s = 0, iter = 0, gk = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
                 const int z = t / tiles_mn;
@@ -650,40 +669,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                 mbar_wait(acc_empty(b), ((uint32_t)(iter >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
-                for (int i = 0; i < nkb; ++i) {
+                for (int i = 0; i < nkb; ++i, ++gk) {
+                    if (lane == 0) TC_TRACE(0, gk, 0);
                     mbar_wait(full_a(s), ph);
+                    if (lane == 0) TC_TRACE(0, gk, 1);
                     mbar_wait(full_b(s), ph);
+                    if (lane == 0) TC_TRACE(0, gk, 2);
                     tc_fence_after();
                     const uint32_t a_hi = sbase + (uint32_t)s * STAGE_BYTES;
                     const uint32_t a_lo = a_hi + TC_A_TILE;
                     const uint32_t b_hi = a_hi + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
                     const uint32_t b_lo = b_hi + B_TILE;
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) {
-                        if (dbg & 8) break;
-                        const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
-                        if (NPASS == 3) {
-                            // small terms first, so the big hi*hi product is added to an already-formed correction
-                            const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
-                            umma_tf32(tmem_acc, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                            umma_tf32(tmem_acc, da_hi, db_lo, idesc, 1u);
-                            umma_tf32(tmem_acc, da_hi, db_hi, idesc, 1u);
-                        } else {
-                            umma_tf32(tmem_acc, da_hi, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < TC_BK / 8; ++k) {
+                            if (dbg & 8) break;
+                            const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
+                            if (NPASS == 3) {
+                                // small terms first, so the big hi*hi product is added to an already-formed correction
+                                const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
+                                umma_tf32(tmem_acc, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                                umma_tf32(tmem_acc, da_hi, db_lo, idesc, 1u);
+                                umma_tf32(tmem_acc, da_hi, db_hi, idesc, 1u);
+                            } else {
+                                umma_tf32(tmem_acc, da_hi, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(empty(s));            // slot free once these MMAs have read it
+                        if (i == nkb - 1) umma_commit(acc_full(b));   // accumulator complete
                     }
-                    umma_commit(empty(s));            // slot free once these MMAs have read it
+                    __syncwarp();
+                    if (lane == 0) TC_TRACE(0, gk, 3);
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(acc_full(b));             // accumulator complete
             }
         }
-        __syncwarp();
     } else {
-        // ===================== weight-tile bulk copies (one thread) =====================
-        if (lane == 0) {
+        // ===================== weight-tile bulk copies (whole warp convergent, one elected lane issues) =====================
+        {
             constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
-            int s = 0;
+            int s = 0, gk = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
                 const int z = t / tiles_mn, mn = t - z * tiles_mn;
@@ -691,19 +716,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                 const int kb0 = z * ts.kb_per_split;
                 const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
                 const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * ts.nkb_total + kb0) * (2 * B_TILE);
-                for (int i = 0; i < nkb; ++i) {
+                for (int i = 0; i < nkb; ++i, ++gk) {
+                    if (lane == 0) TC_TRACE(2, gk, 0);
                     mbar_wait(empty(s), ph ^ 1u);
+                    if (lane == 0) TC_TRACE(2, gk, 1);
                     const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
-                    if (dbg & 1) { mbar_arrive(full_b(s)); }
-                    else {
-                        mbar_arrive_expect_tx(full_b(s), bytes);
-                        bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
+                    if (elect_one_sync()) {
+                        if (dbg & 1) { mbar_arrive(full_b(s)); }
+                        else {
+                            mbar_arrive_expect_tx(full_b(s), bytes);
+                            bulk_g2s(dst, src + (size_t)i * (2 * B_TILE), bytes, full_b(s));
+                        }
                     }
+                    __syncwarp();
                     if (++s == stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
-        __syncwarp();
     }
     __syncthreads();
     if (warp == TC_AUX_WARP) {
@@ -832,7 +861,9 @@ static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
     if (dbg < 0) { const char* e = getenv("DEFT_TC_DBG"); dbg = e ? atoi(e) : 0; }
     if (const char* e = getenv("DEFT_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) { stages = v; } }
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
-    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, stages, epi, dbg);
+    long long* trace = nullptr;
+    if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
+    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, stages, epi, dbg, trace);
     DEFT_CHECK_LAUNCH("tc_igemm_kernel");
     return DEFT_OK;
 }
