@@ -741,6 +741,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     }
 }
 
+}  // namespace deft
+#include "tc_ts.cuh"
+namespace deft {
+
 // Deterministic split-K tail: out = epilogue(sum_z partial[z]).
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int ldp, Epilogue e) {
     const int c4 = e.Cout / 4;
@@ -900,6 +904,38 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     return DEFT_OK;
 }
 
+template <class AP>
+static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                       size_t scratch_bytes, cudaStream_t st) {
+    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0 || K % TC_BK != 0) return DEFT_EINVAL;
+    const int nkb = K / TC_BK, nt = ldw / bn;
+    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
+    if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
+    if (splits > 1) splits = ceil_div(nkb, ceil_div(nkb, splits));
+    EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
+    const bool x1 = (flags & DEFT_FLAG_TF32X1) != 0;
+    int rc = DEFT_EINVAL;
+#define TS_CASE(BNV)                                                                          \
+    case BNV:                                                                                 \
+        rc = x1 ? ts_launch<AP, BNV, 1>(ap, blob, nkb, M, nt, splits, epi, st)                \
+                : ts_launch<AP, BNV, 3>(ap, blob, nkb, M, nt, splits, epi, st);               \
+        break;
+    switch (bn) {
+        TS_CASE(128)
+        TS_CASE(64)
+        TS_CASE(32)
+        TS_CASE(16)
+    }
+#undef TS_CASE
+    if (rc != DEFT_OK || splits == 1) return rc;
+    size_t total = (size_t)M * (ep.Cout / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    DEFT_CHECK_LAUNCH("splitk_reduce");
+    return DEFT_OK;
+}
+
 static TcConvFastAP make_fast_ap(const ConvAP& ap) {
     TcConvFastAP f{};
     f.src = ap.src[0]; f.pitch = ap.pitch[0]; f.H = ap.H; f.W = ap.W; f.OH = ap.OH; f.OW = ap.OW;
@@ -911,6 +947,17 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
                      size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
         if (ap.c[i] % 4 != 0) return DEFT_EINVAL;
+    if (ts_enabled() && bn <= 128 && ap.KH * ap.KW <= 9 && ap.Ctot % TC_BK == 0 && ap.Ctot / TC_BK <= 64) {
+        bool ok = true;                                    // every source a multiple of 32 channels: a k-block never straddles sources
+        for (int i = 0; i < ap.nsrc; ++i) ok = ok && (ap.c[i] % TC_BK == 0);
+        if (ok) {
+            TsConvAP t{};
+            t.a = ap;
+            t.taps = ap.KH * ap.KW;
+            t.ncb = ap.Ctot / TC_BK;
+            return ts_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+        }
+    }
     if (ap.nsrc == 1 && ap.Ctot % TC_BK == 0 && ap.KH * ap.KW <= 9) {
         // fast path: single source, channel-block-major K (what tc_k_perm_taps prescribes for Ctot % 32 == 0) or 1x1
         return tc_dispatch(make_fast_ap(ap), blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
@@ -925,6 +972,11 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
 int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                     size_t scratch_bytes, cudaStream_t st) {
     if (ap.Cin % 32 != 0 || bn > 64) return DEFT_EINVAL;
+    if (ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
+        TsDcnAP d{};
+        d.a = ap;
+        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+    }
     TcDcnAP t{};
     t.a = ap;
     t.K = K;
@@ -932,6 +984,11 @@ int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, 
 }
 
 int tc_pair_dispatch(const PairAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
+    if (ts_enabled() && bn <= 128 && K % TC_BK == 0) {
+        TsPairAP d{};
+        d.a = ap;
+        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, nullptr, 0, st);
+    }
     TcPairAP t{};
     t.a = ap;
     t.K = K;
