@@ -26,7 +26,8 @@ constexpr int TC_PWARPS = 16;                   // A-producer warps
 constexpr int TC_EWARPS = 4;                    // epilogue warps (one per TMEM lane quadrant)
 constexpr int TC_PRODUCERS = TC_PWARPS * 32;
 constexpr int TC_MMA_WARP = TC_PWARPS + TC_EWARPS;
-constexpr int TC_AUX_WARP = TC_MMA_WARP + 1;    // TMEM allocator + weight-tile bulk copies
+constexpr int TC_MMA_WARPS = 2;                 // the TS kernel alternates k-blocks between two issuer warps
+constexpr int TC_AUX_WARP = TC_MMA_WARP + TC_MMA_WARPS;    // TMEM allocator + weight-tile bulk copies
 constexpr int TC_THREADS = (TC_AUX_WARP + 1) * 32;
 constexpr int TC_A_TILE = TC_BM * 128;          // bytes
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                 }
             }
         }
-    } else {
+    } else if (warp == TC_AUX_WARP) {
         // ===================== weight-tile bulk copies (whole warp convergent, one elected lane issues) =====================
         {
             constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
@@ -972,7 +973,9 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
 int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                     size_t scratch_bytes, cudaStream_t st) {
     if (ap.Cin % 32 != 0 || bn > 64) return DEFT_EINVAL;
-    if (ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
+    static int ts_dcn = -1;
+    if (ts_dcn < 0) { const char* e = getenv("DEFT_TC_TS_DCN"); ts_dcn = e ? atoi(e) : 0; }
+    if (ts_dcn && ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
         TsDcnAP d{};
         d.a = ap;
         return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);

@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     auto b_empty = [&](int s) { return bar_base + 8u * (24 + s); };
     auto acc_full = [&](int b) { return bar_base + 8u * (32 + b); };
     auto acc_empty = [&](int b) { return bar_base + 8u * (34 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * 36;
+    auto tile_go = [&](int b) { return bar_base + 8u * (36 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * 38;
     unsigned char* ap_extra = smem + (size_t)sb * Cfg::B_STAGE + 512;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,8 +251,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             mbar_init(b_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(acc_full(b), 1);
+            mbar_init(acc_full(b), TC_MMA_WARPS);         // one commit (or plain arrive) per issuer warp
             mbar_init(acc_empty(b), TC_EWARPS);
+            mbar_init(tile_go(b), 1);
         }
         fence_mbar_init();
         fence_proxy_async();
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)sb * Cfg::B_STAGE + 8 * 36);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)sb * Cfg::B_STAGE + 8 * 38);
     const int tiles_mn = ts.m_tiles * ts.n_tiles;
 
     if (warp < TC_PWARPS) {
@@ -337,27 +339,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             if (lane == 0) mbar_arrive(acc_empty(b));
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 2);
         }
-    } else if (warp == TC_MMA_WARP) {
-        // ===================== MMA issuer: A from TMEM, B from smem =====================
+    } else if (warp < TC_AUX_WARP) {
+        // ===================== two MMA issuer warps (A from TMEM, B from smem), alternating k-blocks =====================
+        // tcgen05.mma issue blocks the issuing thread for roughly the MMA's duration (measured ~46 cycles for 128x64x8),
+        // so a single issuer leaves the tensor pipe idle during its own barrier waits / commits; two issuers hide that.
+        // Accumulation order between k-blocks is irrelevant except for the zero-initialising first MMA of a tile, which
+        // issuer 0 owns; issuer 1 waits on tile_go until that k-block has completed.
         constexpr uint32_t idesc = make_idesc(BN);
-        int iter = 0, gk = 0, s_b = 0;
-        uint32_t ph_b = 0;
+        const int w = warp - TC_MMA_WARP;
+        int iter = 0, gk0 = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn;
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             const int b = iter & 1;
-            mbar_wait(acc_empty(b), ((uint32_t)(iter >> 1) & 1u) ^ 1u);
+            const uint32_t tile_par = (uint32_t)(iter >> 1) & 1u;
+            mbar_wait(acc_empty(b), tile_par ^ 1u);
+            if (w == 1 && nkb > 1) mbar_wait(tile_go(b), tile_par);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
-            for (int i = 0; i < nkb; ++i, ++gk) {
+            for (int i = w; i < nkb; i += TC_MMA_WARPS) {
+                const int gk = gk0 + i;
                 const int sa = gk % SA;
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
-                if (lane == 0) TC_TRACE(0, gk, 0);
+                const int s_b = gk % sb;
+                const uint32_t ph_b = (uint32_t)(gk / sb) & 1u;
+                if (lane == 0 && w == 0) TC_TRACE(0, gk, 0);
                 mbar_wait(a_full(sa), pa);
-                if (lane == 0) TC_TRACE(0, gk, 1);
+                if (lane == 0 && w == 0) TC_TRACE(0, gk, 1);
                 mbar_wait(b_full(s_b), ph_b);
-                if (lane == 0) TC_TRACE(0, gk, 2);
+                if (lane == 0 && w == 0) TC_TRACE(0, gk, 2);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
                 const uint32_t a_lo = a_hi + 32u;
@@ -379,14 +390,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
                     }
                     umma_commit(a_empty(sa));
                     umma_commit(b_empty(s_b));
-                    if (i == nkb - 1) umma_commit(acc_full(b));
+                    if (i == 0) umma_commit(tile_go(b));                 // issuer 1 may start accumulating
+                    if (i + TC_MMA_WARPS >= nkb) umma_commit(acc_full(b));   // this issuer's share of the tile is in flight
                 }
                 __syncwarp();
-                if (lane == 0) TC_TRACE(0, gk, 3);
-                if (++s_b == sb) { s_b = 0; ph_b ^= 1u; }
+                if (lane == 0 && w == 0) TC_TRACE(0, gk, 3);
             }
+            if (w == 1 && nkb < 2 && lane == 0) mbar_arrive(acc_full(b));   // no k-block for issuer 1 in this tile
+            gk0 += nkb;
         }
-    } else {
+    } else if (warp == TC_AUX_WARP) {
         // ===================== weight-tile bulk copies =====================
         int s_b = 0, gk = 0;
         uint32_t ph_b = 0;
