@@ -974,7 +974,7 @@ int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, 
                     size_t scratch_bytes, cudaStream_t st) {
     if (ap.Cin % 32 != 0 || bn > 64) return DEFT_EINVAL;
     static int ts_dcn = -1;
-    if (ts_dcn < 0) { const char* e = getenv("DEFT_TC_TS_DCN"); ts_dcn = e ? atoi(e) : 0; }
+    if (ts_dcn < 0) { const char* e = getenv("DEFT_TC_TS_DCN"); ts_dcn = e ? atoi(e) : 1; }
     if (ts_dcn && ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
         TsDcnAP d{};
         d.a = ap;

@@ -30,11 +30,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 
 // ------------------------------------------------------------------------------------------------ producers
-// Interface (thread = row `row` of the tile, 0..127):
-//   kExtraSmemBytes, BATCH (8-column groups fetched per load() call; 4/BATCH calls per k-block)
-//   setup_once(extra)                      once per kernel, all 512 producer threads (may use named barrier 1)
-//   tile_init(m0, M, extra, row)           once per tile
-//   load(kb, bi, v[BATCH*8])               A[row, kb*32 + bi*BATCH*8 ...] (absolute k-block index kb)
+// A producer warp owns 32 rows (one TMEM lane quadrant) and every 4th k-block.  Per k-block it
+//   1. fill(): loads the rows' 128 B with the COALESCED mapping (8 lanes x 16 B per row, 4 rows per LDG.128) -- the
+//      thread=row mapping tcgen05.st needs would touch 32 cache lines per load instruction (8x the L1 wavefronts,
+//      measured: no gain over the smem-operand kernel) -- and parks them in a private, padded smem stage [32][36];
+//   2. the kernel reads the stage row-wise (lane = row, conflict-free LDS.128), splits hi/lo and tcgen05.st's.
+// Interface:  kExtraSmemBytes; setup_once(extra); tile_init(m0, M, extra, quad, lane, meta) -- meta = this warp's
+// private int4[32] row table in smem; fill(kb, quad, lane, meta, stage).
+constexpr int TS_STAGE_LD = 36;                                   // floats per staged row (32 + 4 pad: conflict-free)
+constexpr int TS_STAGE_FLOATS = 32 * TS_STAGE_LD;
+constexpr int TS_WARP_SMEM = TS_STAGE_FLOATS * 4 + 32 * 16;       // stage + row table, per producer warp
+constexpr int TS_COMMON_SMEM = TC_PWARPS * TS_WARP_SMEM;
 
 // im2col over a channel concat of up to 4 NHWC sources, every channel count a multiple of 32.
 // K order = (32-channel block, tap, channel) (tc_k_perm_taps) or 1x1.
@@ -43,11 +49,8 @@ struct TsConvAP {
     ConvAP a;
     int taps, ncb;
     static constexpr int kExtraSmemBytes = 64 + 64 * 16;
-    static constexpr int BATCH = 4;
     const int* toff_;
     const TsSrcEntry* cbsrc_;
-    int pix_;
-    unsigned vmask_;
     __device__ __forceinline__ void setup_once(unsigned char* extra) {
         int* toff = reinterpret_cast<int*>(extra);
         TsSrcEntry* cbsrc = reinterpret_cast<TsSrcEntry*>(extra + 64);
@@ -66,51 +69,52 @@ struct TsConvAP {
         cbsrc_ = cbsrc;
         asm volatile("bar.sync 1, 512;" ::: "memory");
     }
-    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int row) {
-        const int p = m0 + row;
-        vmask_ = 0;
-        pix_ = 0;
+    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int quad, int lane, int4* meta) {
+        const int p = m0 + quad * 32 + lane;
+        int pix = 0;
+        unsigned vmask = 0;
         if (p < M) {
             const int n = p / (a.OH * a.OW);
             const int r = p - n * (a.OH * a.OW);
             const int oy = (r / a.OW) * a.stride, ox = (r - (r / a.OW) * a.OW) * a.stride;
-            pix_ = (n * a.H + oy) * a.W + ox;
+            pix = (n * a.H + oy) * a.W + ox;
             unsigned bit = 1u;
             for (int ky = 0; ky < a.KH; ++ky)
                 for (int kx = 0; kx < a.KW; ++kx, bit <<= 1) {
                     const int iy = oy - a.pad + ky, ix = ox - a.pad + kx;
-                    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) vmask_ |= bit;
+                    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) vmask |= bit;
                 }
         }
+        meta[lane] = make_int4(pix, (int)vmask, 0, 0);
+        __syncwarp();
     }
-    __device__ __forceinline__ void load(int kb, int, float (&v)[32]) const {
+    __device__ __forceinline__ void fill(int kb, int, int lane, const int4* meta, float* stage) const {
         const int cb = kb / taps, tap = kb - cb * taps;
-        if ((vmask_ >> tap) & 1u) {
-            const TsSrcEntry e = cbsrc_[cb];
-            const float* ptr = e.p + (size_t)(pix_ + toff_[tap]) * e.pitch + e.coff;
+        const TsSrcEntry e = cbsrc_[cb];
+        const int toff = toff_[tap];
+        const int ch = (lane & 7) * 4;
+        const float* base = e.p + e.coff + ch;
+        float4 r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t = ldg4(ptr + 4 * j);
-                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < 8; ++j) {
+            const int4 m = meta[(lane >> 3) + 4 * j];
+            r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((unsigned)m.y >> tap) & 1u) r[j] = ldg4(base + (size_t)(m.x + toff) * e.pitch);
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + ((lane >> 3) + 4 * j) * TS_STAGE_LD + ch) = r[j];
     }
 };
 
 // DCNv2 bilinear gather; K order = (32-channel block, tap, channel).  The 4 corner element-offsets / weights of the
-// tile's 128 rows x 9 taps live in smem (built once per tile by all producers, read by the row's 4 k-group threads).
+// tile's 128 rows x 9 taps live in smem (built once per tile by all producers).
 struct TsDcnAP {
     DcnAP a;
     static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
-    static constexpr int BATCH = 1;
     const int4* tabO_;
     const float4* tabW_;
-    int row_;
     __device__ __forceinline__ void setup_once(unsigned char*) {}
-    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char* extra, int row) {
+    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char* extra, int, int, int4*) {
         int4* tabO = reinterpret_cast<int4*>(extra);
         float4* tabW = reinterpret_cast<float4*>(extra + TC_BM * 9 * 16);
         const int H = a.H, W = a.W;
@@ -147,26 +151,27 @@ struct TsDcnAP {
         }
         tabO_ = tabO;
         tabW_ = tabW;
-        row_ = row;
         asm volatile("bar.sync 1, 512;" ::: "memory");
     }
-    __device__ __forceinline__ void load(int kb, int bi, float (&v)[8]) const {
+    __device__ __forceinline__ void fill(int kb, int quad, int lane, const int4*, float* stage) const {
         const int cb = kb / 9, tap = kb - cb * 9;
-        const int4 o = tabO_[row_ * 9 + tap];
-        const float4 w = tabW_[row_ * 9 + tap];
-        const float* x = a.x + cb * TC_BK + bi * 8;
-        const float4 c00 = ldg4(x + o.x), c01 = ldg4(x + o.x + 4);
-        const float4 c10 = ldg4(x + o.y), c11 = ldg4(x + o.y + 4);
-        const float4 c20 = ldg4(x + o.z), c21 = ldg4(x + o.z + 4);
-        const float4 c30 = ldg4(x + o.w), c31 = ldg4(x + o.w + 4);
-        v[0] = w.x * c00.x + w.y * c10.x + w.z * c20.x + w.w * c30.x;
-        v[1] = w.x * c00.y + w.y * c10.y + w.z * c20.y + w.w * c30.y;
-        v[2] = w.x * c00.z + w.y * c10.z + w.z * c20.z + w.w * c30.z;
-        v[3] = w.x * c00.w + w.y * c10.w + w.z * c20.w + w.w * c30.w;
-        v[4] = w.x * c01.x + w.y * c11.x + w.z * c21.x + w.w * c31.x;
-        v[5] = w.x * c01.y + w.y * c11.y + w.z * c21.y + w.w * c31.y;
-        v[6] = w.x * c01.z + w.y * c11.z + w.z * c21.z + w.w * c31.z;
-        v[7] = w.x * c01.w + w.y * c11.w + w.z * c21.w + w.w * c31.w;
+        const int ch = (lane & 7) * 4;
+        const float* x = a.x + cb * TC_BK + ch;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {                   // two rows (8 corner loads) in flight at a time
+            const int r0 = (lane >> 3) + 8 * jj, r1 = r0 + 4;
+            const int4 o0 = tabO_[(quad * 32 + r0) * 9 + tap], o1 = tabO_[(quad * 32 + r1) * 9 + tap];
+            const float4 w0 = tabW_[(quad * 32 + r0) * 9 + tap], w1 = tabW_[(quad * 32 + r1) * 9 + tap];
+            const float4 a0 = ldg4(x + o0.x), a1 = ldg4(x + o0.y), a2 = ldg4(x + o0.z), a3 = ldg4(x + o0.w);
+            const float4 b0 = ldg4(x + o1.x), b1 = ldg4(x + o1.y), b2 = ldg4(x + o1.z), b3 = ldg4(x + o1.w);
+            float4 u, v;
+            u.x = w0.x * a0.x + w0.y * a1.x + w0.z * a2.x + w0.w * a3.x; u.y = w0.x * a0.y + w0.y * a1.y + w0.z * a2.y + w0.w * a3.y;
+            u.z = w0.x * a0.z + w0.y * a1.z + w0.z * a2.z + w0.w * a3.z; u.w = w0.x * a0.w + w0.y * a1.w + w0.z * a2.w + w0.w * a3.w;
+            v.x = w1.x * b0.x + w1.y * b1.x + w1.z * b2.x + w1.w * b3.x; v.y = w1.x * b0.y + w1.y * b1.y + w1.z * b2.y + w1.w * b3.y;
+            v.z = w1.x * b0.z + w1.y * b1.z + w1.z * b2.z + w1.w * b3.z; v.w = w1.x * b0.w + w1.y * b1.w + w1.z * b2.w + w1.w * b3.w;
+            *reinterpret_cast<float4*>(stage + r0 * TS_STAGE_LD + ch) = u;
+            *reinterpret_cast<float4*>(stage + r1 * TS_STAGE_LD + ch) = v;
+        }
     }
 };
 
@@ -174,35 +179,41 @@ struct TsDcnAP {
 struct TsPairAP {
     PairAP a;
     static constexpr int kExtraSmemBytes = 0;
-    static constexpr int BATCH = 2;
-    const float* pa_;
-    const float* pb_;
     __device__ __forceinline__ void setup_once(unsigned char*) {}
-    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int row) {
-        const int p = m0 + row;
-        pa_ = nullptr;
-        pb_ = nullptr;
+    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int quad, int lane, int4* meta) {
+        const int p = m0 + quad * 32 + lane;
+        long long offa = -1, offb = 0;                     // element offsets into au / bv; -1 = dead row
         if (p < M) {
             int f = 0;
             while (f < a.F - 1 && p >= a.off[f + 1]) ++f;
             int q = p - a.off[f];
             int ii = q / a.m, jj = q - ii * a.m;
-            pa_ = a.au + ((size_t)f * a.P + ii) * a.ld;
-            pb_ = a.bv + (size_t)jj * a.ld;
+            offa = ((long long)f * a.P + ii) * a.ld;
+            offb = (long long)jj * a.ld;
         }
+        meta[lane] = make_int4((int)(offa & 0xffffffffLL), (int)(offa >> 32), (int)(offb & 0xffffffffLL), (int)(offb >> 32));
+        __syncwarp();
     }
-    __device__ __forceinline__ void load(int kb, int bi, float (&v)[16]) const {
-        if (pa_ != nullptr) {
-            const int k = kb * TC_BK + bi * 16;
+    __device__ __forceinline__ void fill(int kb, int, int lane, const int4* meta, float* stage) const {
+        const int k = kb * TC_BK + (lane & 7) * 4;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            float4 xa[4], xb[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 x = ldg4(pa_ + k + 4 * j), y = ldg4(pb_ + k + 4 * j);
-                v[4 * j] = fmaxf(x.x + y.x, 0.f); v[4 * j + 1] = fmaxf(x.y + y.y, 0.f);
-                v[4 * j + 2] = fmaxf(x.z + y.z, 0.f); v[4 * j + 3] = fmaxf(x.w + y.w, 0.f);
+                const int4 m = meta[(lane >> 3) + 4 * (jj * 4 + j)];
+                const long long offa = ((long long)m.y << 32) | (unsigned)m.x, offb = ((long long)m.w << 32) | (unsigned)m.z;
+                xa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (offa >= 0) { xa[j] = ldg4(a.au + offa + k); xb[j] = ldg4(a.bv + offb + k); }
             }
-        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            for (int j = 0; j < 4; ++j) {
+                float4 v;
+                v.x = fmaxf(xa[j].x + xb[j].x, 0.f); v.y = fmaxf(xa[j].y + xb[j].y, 0.f);
+                v.z = fmaxf(xa[j].z + xb[j].z, 0.f); v.w = fmaxf(xa[j].w + xb[j].w, 0.f);
+                *reinterpret_cast<float4*>(stage + ((lane >> 3) + 4 * (jj * 4 + j)) * TS_STAGE_LD + (lane & 7) * 4) = v;
+            }
         }
     }
 };
@@ -240,7 +251,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     auto acc_empty = [&](int b) { return bar_base + 8u * (34 + b); };
     auto tile_go = [&](int b) { return bar_base + 8u * (36 + b); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
-    unsigned char* ap_extra = smem + (size_t)sb * Cfg::B_STAGE + 512;
+    unsigned char* ap_common = smem + (size_t)sb * Cfg::B_STAGE + 512;     // per-warp transpose stages + row tables
+    unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -266,10 +278,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     const int tiles_mn = ts.m_tiles * ts.n_tiles;
 
     if (warp < TC_PWARPS) {
-        // ===================== A producers: thread = row, warp = (quadrant, k-group) =====================
+        // ===================== A producers: warp = (TMEM lane quadrant, k-group) =====================
         const int quad = warp & 3, grp = warp >> 2;
-        const int row = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        float* stage = reinterpret_cast<float*>(ap_common + (size_t)warp * TS_WARP_SMEM);
+        int4* meta = reinterpret_cast<int4*>(ap_common + (size_t)warp * TS_WARP_SMEM + TS_STAGE_FLOATS * 4);
         ap.setup_once(ap_extra);
         int gk0 = 0;                                      // global k-block counter at the start of the tile
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             const int m0 = (mn / ts.n_tiles) * TC_BM;
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
-            ap.tile_init(m0, M, ap_extra, row);
+            ap.tile_init(m0, M, ap_extra, quad, lane, meta);
             // this group's k-blocks: global index gk with gk % TS_KGROUPS == grp
             int i = (grp - (gk0 % TS_KGROUPS) + TS_KGROUPS) % TS_KGROUPS;
             for (; i < nkb; i += TS_KGROUPS) {
@@ -286,36 +299,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
                 const uint32_t acol = tmem_base + lane_addr + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
                 if (tid == grp * 128) TC_TRACE(1, gk, 0);
-                bool waited = false;
+                if (!(dbg & 2)) ap.fill(kb0 + i, quad, lane, meta, stage);     // coalesced loads -> private smem stage
+                __syncwarp();
+                if (tid == grp * 128) TC_TRACE(1, gk, 1);
+                mbar_wait(a_empty(sa), pa ^ 1u);
+                tc_fence_after();
+                if (tid == grp * 128) TC_TRACE(1, gk, 2);
+                if (!(dbg & 4)) {
 #pragma unroll
-                for (int bi = 0; bi < 4 / AP::BATCH; ++bi) {
-                    float v[AP::BATCH * 8];
-                    if (!(dbg & 2)) ap.load(kb0 + i, bi, v);
-                    if (!waited) {                         // the first loads are in flight while we wait for the slot
-                        if (tid == grp * 128) TC_TRACE(1, gk, 1);
-                        mbar_wait(a_empty(sa), pa ^ 1u);
-                        tc_fence_after();
-                        if (tid == grp * 128) TC_TRACE(1, gk, 2);
-                        waited = true;
-                    }
-                    if (dbg & 4) continue;
-#pragma unroll
-                    for (int q = 0; q < AP::BATCH; ++q) {
+                    for (int q = 0; q < 4; ++q) {          // lane = row: 8 columns at a time
+                        const float4 x0 = *reinterpret_cast<const float4*>(stage + lane * TS_STAGE_LD + q * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(stage + lane * TS_STAGE_LD + q * 8 + 4);
+                        const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                         float hi[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) hi[j] = tf32_rna(v[q * 8 + j]);
-                        tmem_st8(acol + (uint32_t)((bi * AP::BATCH + q) * 8), hi);
+                        for (int j = 0; j < 8; ++j) hi[j] = tf32_rna(v[j]);
+                        tmem_st8(acol + (uint32_t)(q * 8), hi);
                         if (NPASS == 3) {
                             float lo[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) lo[j] = v[q * 8 + j] - hi[j];
-                            tmem_st8(acol + 32u + (uint32_t)((bi * AP::BATCH + q) * 8), lo);
+                            for (int j = 0; j < 8; ++j) lo[j] = v[j] - hi[j];
+                            tmem_st8(acol + 32u + (uint32_t)(q * 8), lo);
                         }
                     }
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                __syncwarp();
+                __syncwarp();                              // also: everyone has read the stage before the next fill
                 if (lane == 0) mbar_arrive(a_full(sa));
                 if (tid == grp * 128) TC_TRACE(1, gk, 3);
             }
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
 template <class AP, int BN, int NPASS>
 static int ts_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st) {
     using Cfg = TsCfg<BN, NPASS>;
-    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + AP::kExtraSmemBytes;
+    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_COMMON_SMEM + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
     ts.splits = ceil_div(nkb, ts.kb_per_split);
