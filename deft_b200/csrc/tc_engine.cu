@@ -434,7 +434,9 @@ struct EpiStd {
     int ldp;
     static constexpr int kSmemBytes = 0;
     template <int BN>
-    __device__ __forceinline__ void run(uint32_t tmem_acc, unsigned char*, int ewarp, int lane, int m0, int M, int ntile, int z) const {
+    __device__ __forceinline__ void run(uint32_t tmem_acc, unsigned char*, int ewarp, int lane, int m0, int M, int ntile, int z,
+                                        uint32_t acc2_cols = 0u) const {
+        // acc2_cols != 0: a second partial accumulator sits acc2_cols columns further (TS kernel, one per MMA issuer)
         constexpr int LW = BN >= 32 ? 32 : BN;                // columns per tcgen05.ld
         const int lane_base = ewarp * 32;
         const int p = m0 + lane_base + lane;
@@ -442,6 +444,12 @@ struct EpiStd {
         for (int c = 0; c < BN; c += LW) {
             float v[LW];
             tmem_ld<LW>(tmem_acc + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+            if (acc2_cols) {
+                float v2[LW];
+                tmem_ld<LW>(tmem_acc + acc2_cols + ((uint32_t)lane_base << 16) + (uint32_t)c, v2);
+#pragma unroll
+                for (int j = 0; j < LW; ++j) v[j] += v2[j];
+            }
             const int co = ntile * BN + c;
             if (p >= M) continue;
             if (partial != nullptr) {

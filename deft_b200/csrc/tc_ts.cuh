@@ -220,11 +220,18 @@ struct TsPairAP {
 
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across producer warp groups
+// Two MMA issuer warps alternate k-blocks (tcgen05.mma issue blocks the issuing thread, so one issuer leaves the tensor
+// pipe idle during its own barrier waits and commits: 53 -> 43 us on the 64->64 3x3 layer).  Each issuer accumulates
+// into its OWN TMEM accumulator and the epilogue adds the two in a fixed order: with a shared accumulator the order in
+// which the two issuers' MMAs land is timing dependent and results stop being bit-identical run to run
+// (tests/test_gpu_frame.py::test_c2_full_size_properties caught exactly that).
+constexpr int TS_ISSUERS = 2;
 
 template <int BN, int NPASS>
 struct TsCfg {
     static constexpr int ACOLS = NPASS == 3 ? 64 : 32;                 // TMEM columns of one A stage (hi [+ lo])
-    static constexpr int A0 = 2 * BN;                                   // first A column (after the 2 accumulators)
+    static constexpr int NBUF = (2 * TS_ISSUERS * BN <= 256) ? 2 : 1;   // accumulator sets (double-buffered across tiles when they fit)
+    static constexpr int A0 = NBUF * TS_ISSUERS * BN;                   // first A column (after the accumulators)
     static constexpr int SA_RAW = (512 - A0) / ACOLS;
     static constexpr int SA = SA_RAW > 6 ? 6 : SA_RAW;                  // A ring depth
     static constexpr int B_TILE = BN * 128;
@@ -249,7 +256,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     auto b_empty = [&](int s) { return bar_base + 8u * (24 + s); };
     auto acc_full = [&](int b) { return bar_base + 8u * (32 + b); };
     auto acc_empty = [&](int b) { return bar_base + 8u * (34 + b); };
-    auto tile_go = [&](int b) { return bar_base + 8u * (36 + b); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
     unsigned char* ap_common = smem + (size_t)sb * Cfg::B_STAGE + 512;     // per-warp transpose stages + row tables
     unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
@@ -263,9 +269,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             mbar_init(b_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(acc_full(b), TC_MMA_WARPS);         // one commit (or plain arrive) per issuer warp
+            mbar_init(acc_full(b), TS_ISSUERS);           // one commit (or plain arrive) per issuer warp
             mbar_init(acc_empty(b), TC_EWARPS);
-            mbar_init(tile_go(b), 1);
         }
         fence_mbar_init();
         fence_proxy_async();
@@ -338,12 +343,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
             const int m0 = (mn / ts.n_tiles) * TC_BM, ntile = mn % ts.n_tiles;
-            const int b = iter & 1;
+            const int b = iter % Cfg::NBUF;
+            const int kb0 = z * ts.kb_per_split;
+            const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 0);
-            mbar_wait(acc_full(b), (uint32_t)(iter >> 1) & 1u);
+            mbar_wait(acc_full(b), (uint32_t)(iter / Cfg::NBUF) & 1u);
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
-            if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * BN), nullptr, ewarp, lane, m0, M, ntile, z);
+            // issuer 1's accumulator holds a partial sum only when the tile has >= 2 k-blocks
+            if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), nullptr, ewarp, lane, m0, M, ntile, z,
+                                                  (TS_ISSUERS > 1 && nkb > 1) ? (uint32_t)BN : 0u);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(b));
@@ -351,10 +360,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
         }
     } else if (warp < TC_AUX_WARP) {
         // ===================== two MMA issuer warps (A from TMEM, B from smem), alternating k-blocks =====================
-        // tcgen05.mma issue blocks the issuing thread for roughly the MMA's duration (measured ~46 cycles for 128x64x8),
-        // so a single issuer leaves the tensor pipe idle during its own barrier waits / commits; two issuers hide that.
-        // Accumulation order between k-blocks is irrelevant except for the zero-initialising first MMA of a tile, which
-        // issuer 0 owns; issuer 1 waits on tile_go until that k-block has completed.
+        // tcgen05.mma issue blocks the issuing thread for roughly the MMA's duration (measured ~46 cycles for 128x64x8).
+        // Issuer w owns k-blocks w, w+2, ... of every tile and accumulator column block w of the tile's set.
         constexpr uint32_t idesc = make_idesc(BN);
         const int w = warp - TC_MMA_WARP;
         int iter = 0, gk0 = 0;
@@ -362,13 +369,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             const int z = t / tiles_mn;
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
-            const int b = iter & 1;
-            const uint32_t tile_par = (uint32_t)(iter >> 1) & 1u;
+            const int b = iter % Cfg::NBUF;
+            const uint32_t tile_par = (uint32_t)(iter / Cfg::NBUF) & 1u;
             mbar_wait(acc_empty(b), tile_par ^ 1u);
-            if (w == 1 && nkb > 1) mbar_wait(tile_go(b), tile_par);
             tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
-            for (int i = w; i < nkb; i += TC_MMA_WARPS) {
+            const uint32_t tmem_acc = tmem_base + (uint32_t)((b * TS_ISSUERS + w) * BN);
+            for (int i = w; i < nkb; i += TS_ISSUERS) {
                 const int gk = gk0 + i;
                 const int sa = gk % SA;
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
@@ -391,22 +397,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
                         const uint64_t db_hi = make_smem_desc(b_hi + k * 32);
                         if (NPASS == 3) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);
-                            umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > w || k > 0) ? 1u : 0u);
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_lo, idesc, 1u);
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, 1u);
                         } else {
-                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, (i > w || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(a_empty(sa));
                     umma_commit(b_empty(s_b));
-                    if (i == 0) umma_commit(tile_go(b));                 // issuer 1 may start accumulating
-                    if (i + TC_MMA_WARPS >= nkb) umma_commit(acc_full(b));   // this issuer's share of the tile is in flight
+                    if (i + TS_ISSUERS >= nkb) umma_commit(acc_full(b));     // this issuer's share of the tile is in flight
                 }
                 __syncwarp();
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 3);
             }
-            if (w == 1 && nkb < 2 && lane == 0) mbar_arrive(acc_full(b));   // no k-block for issuer 1 in this tile
+            if (w >= nkb && lane == 0) mbar_arrive(acc_full(b));    // no k-block for this issuer in the tile
             gk0 += nkb;
         }
     } else if (warp == TC_AUX_WARP) {
