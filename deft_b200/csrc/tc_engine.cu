@@ -15,6 +15,8 @@
 // * Warp roles: warps 0-7 A producers then epilogue (tcgen05.ld -> epilogue functor), warp 8 lane 0 MMA
 //   issuer, warp 9 TMEM allocator + lane 0 weight-tile bulk copies.  mbarrier ring of S stages:
 //   full_a (256 producer arrivals), full_b (tx bytes), empty (tcgen05.commit).
+#include <cuda.h>
+#include <type_traits>
 #include "tc_engine.cuh"
 #include <stdlib.h>
 
@@ -28,7 +30,7 @@ constexpr int TC_PRODUCERS = TC_PWARPS * 32;
 constexpr int TC_MMA_WARP = TC_PWARPS + TC_EWARPS;
 constexpr int TC_MMA_WARPS = 2;                 // the TS kernel alternates k-blocks between two issuer warps
 constexpr int TC_AUX_WARP = TC_MMA_WARP + TC_MMA_WARPS;    // TMEM allocator + weight-tile bulk copies
-constexpr int TC_THREADS = (TC_AUX_WARP + 1) * 32;
+constexpr int TC_THREADS = (TC_AUX_WARP + 2) * 32;   // + the TS kernel's halo-patch TMA loader warp
 constexpr int TC_A_TILE = TC_BM * 128;          // bytes
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
 constexpr int TC_NUM_SMS = 148;
@@ -436,10 +438,15 @@ struct EpiStd {
     template <int BN>
     __device__ __forceinline__ void run(uint32_t tmem_acc, unsigned char*, int ewarp, int lane, int m0, int M, int ntile, int z,
                                         uint32_t acc2_cols = 0u) const {
+        const int p = m0 + ewarp * 32 + lane;
+        run_p<BN>(tmem_acc, ewarp, p, p < M, M, ntile, z, acc2_cols);
+    }
+    // this thread's accumulator row belongs to output pixel p (ignored when !valid)
+    template <int BN>
+    __device__ __forceinline__ void run_p(uint32_t tmem_acc, int ewarp, int p, bool valid, int M, int ntile, int z, uint32_t acc2_cols) const {
         // acc2_cols != 0: a second partial accumulator sits acc2_cols columns further (TS kernel, one per MMA issuer)
         constexpr int LW = BN >= 32 ? 32 : BN;                // columns per tcgen05.ld
         const int lane_base = ewarp * 32;
-        const int p = m0 + lane_base + lane;
 #pragma unroll 1
         for (int c = 0; c < BN; c += LW) {
             float v[LW];
@@ -451,7 +458,7 @@ struct EpiStd {
                 for (int j = 0; j < LW; ++j) v[j] += v2[j];
             }
             const int co = ntile * BN + c;
-            if (p >= M) continue;
+            if (!valid) continue;
             if (partial != nullptr) {
                 float* dst = partial + ((size_t)z * M + p) * ldp + co;
 #pragma unroll
@@ -952,10 +959,87 @@ static TcConvFastAP make_fast_ap(const ConvAP& ap) {
     return f;
 }
 
+// ---- patch path (TsPatchAP): 3x3 / stride 1 / pad 1, one source, Cin % 32 == 0, and a map that tiles into 16x8
+// patches without wasting more than ~15 % of the MMA rows.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+    static TmapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TmapEncodeFn>(p);
+    }
+    return fn;
+}
+static bool patch_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DEFT_TC_PATCH"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+static bool patch_eligible(const ConvAP& ap) {
+    if (!patch_enabled() || ap.nsrc != 1 || ap.KH != 3 || ap.KW != 3 || ap.stride != 1 || ap.pad != 1 || ap.Ctot % TC_BK != 0) return false;
+    if (ap.OH != ap.H || ap.OW != ap.W || ap.pitch[0] % 4 != 0 || (reinterpret_cast<uintptr_t>(ap.src[0]) & 15) != 0) return false;
+    const long long rows = (long long)ceil_div(ap.W, TP_PW) * ceil_div(ap.H, TP_PH) * TC_BM;
+    return rows * 100 <= (long long)ap.H * ap.W * 115;
+}
+static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                          size_t scratch_bytes, cudaStream_t st) {
+    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0) return DEFT_EINVAL;
+    TmapEncodeFn enc = tmap_encoder();
+    if (enc == nullptr) return DEFT_EINVAL;
+    TsPatchAP t{};
+    t.H = ap.H; t.W = ap.W;
+    t.tiles_x = ceil_div(ap.W, TP_PW);
+    t.tiles_y = ceil_div(ap.H, TP_PH);
+    const cuuint64_t gdim[4] = {(cuuint64_t)ap.Ctot, (cuuint64_t)ap.W, (cuuint64_t)ap.H, (cuuint64_t)ap.N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ap.pitch[0] * 4, (cuuint64_t)ap.W * ap.pitch[0] * 4, (cuuint64_t)ap.H * ap.W * ap.pitch[0] * 4};
+    const cuuint32_t box[4] = {TC_BK, TP_HW, TP_HH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ap.src[0]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return DEFT_EINVAL;
+    const int nkb = K / TC_BK, nt = ldw / bn, ncb = ap.Ctot / TC_BK;
+    const int m_tiles = ap.N * t.tiles_x * t.tiles_y;
+    int splits = tc_pick_splits(m_tiles * nt, nkb);
+    if (splits > ncb) splits = ncb;
+    if (splits > 1) splits = ceil_div(ncb, ceil_div(ncb, splits));     // whole channel blocks per split
+    if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
+    EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
+    const bool x1 = (flags & DEFT_FLAG_TF32X1) != 0;
+    int rc = DEFT_EINVAL;
+#define TP_CASE(BNV)                                                                                   \
+    case BNV:                                                                                          \
+        rc = x1 ? ts_launch<TsPatchAP, BNV, 1>(t, blob, nkb, M, nt, splits, epi, st, m_tiles)          \
+                : ts_launch<TsPatchAP, BNV, 3>(t, blob, nkb, M, nt, splits, epi, st, m_tiles);         \
+        break;
+    switch (bn) {
+        TP_CASE(128)
+        TP_CASE(64)
+        TP_CASE(32)
+        TP_CASE(16)
+    }
+#undef TP_CASE
+    if (rc != DEFT_OK || splits == 1) return rc;
+    size_t total = (size_t)M * (ep.Cout / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    DEFT_CHECK_LAUNCH("splitk_reduce");
+    return DEFT_OK;
+}
+
 int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                      size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
         if (ap.c[i] % 4 != 0) return DEFT_EINVAL;
+    if (ts_enabled() && patch_eligible(ap) && K == 9 * ap.Ctot) {
+        int rc = patch_dispatch(ap, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+        if (rc != DEFT_EINVAL) return rc;
+    }
     if (ts_enabled() && bn <= 128 && ap.KH * ap.KW <= 9 && ap.Ctot % TC_BK == 0 && ap.Ctot / TC_BK <= 64) {
         bool ok = true;                                    // every source a multiple of 32 channels: a k-block never straddles sources
         for (int i = 0; i < ap.nsrc; ++i) ok = ok && (ap.c[i] % TC_BK == 0);

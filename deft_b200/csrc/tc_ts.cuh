@@ -46,6 +46,7 @@ constexpr int TS_COMMON_SMEM = TC_PWARPS * TS_WARP_SMEM;
 // K order = (32-channel block, tap, channel) (tc_k_perm_taps) or 1x1.
 struct TsSrcEntry { const float* p; int pitch; int coff; };
 struct TsConvAP {
+    static constexpr bool kPatch = false;
     ConvAP a;
     int taps, ncb;
     static constexpr int kExtraSmemBytes = 64 + 64 * 16;
@@ -109,6 +110,7 @@ struct TsConvAP {
 // DCNv2 bilinear gather; K order = (32-channel block, tap, channel).  The 4 corner element-offsets / weights of the
 // tile's 128 rows x 9 taps live in smem (built once per tile by all producers).
 struct TsDcnAP {
+    static constexpr bool kPatch = false;
     DcnAP a;
     static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
     const int4* tabO_;
@@ -177,6 +179,7 @@ struct TsDcnAP {
 
 // Affinity MLP layer 2: A[p, k] = relu(Au'[f(p), i(p), k] + Bv'[j(p), k]) over the live pairs.
 struct TsPairAP {
+    static constexpr bool kPatch = false;
     PairAP a;
     static constexpr int kExtraSmemBytes = 0;
     __device__ __forceinline__ void setup_once(unsigned char*) {}
@@ -218,6 +221,34 @@ struct TsPairAP {
     }
 };
 
+// 3x3 / stride 1 / pad 1 convolution over ONE NHWC source with Cin % 32 == 0: the "patch" producer.
+// An M tile is a 16 x 8 pixel patch of the output (not 128 consecutive pixels), so the 9 taps of a 32-channel block
+// all read the same (16+2) x (8+2) input halo patch.  One TMA tensor copy (box {32 ch, 18, 10, 1}, SWIZZLE_128B,
+// out-of-bounds = zero fill = the conv's zero padding) per (tile, channel block) lands it in shared memory; producer
+// thread = output pixel reads its tap's 128 B with conflict-free LDS.128 (the TMA swizzle spreads 8 consecutive
+// pixels over all banks), splits hi/lo and tcgen05.st's.  No address tables, no global-load latency in the producers,
+// and the input is fetched from L2 ~1.4x instead of 9x.
+constexpr int TP_PW = 16, TP_PH = 8;                               // output patch
+constexpr int TP_HW = TP_PW + 2, TP_HH = TP_PH + 2;                // halo patch
+constexpr int TP_BOX_BYTES = TP_HW * TP_HH * 128;                  // 23040: what one TMA copy delivers
+constexpr int TP_STAGE_BYTES = (TP_BOX_BYTES + 1023) / 1024 * 1024;   // ring stages stay 1024 B aligned (swizzle atom)
+constexpr int TP_MAX_STAGES = 4;
+struct TsPatchAP {
+    static constexpr bool kPatch = true;
+    static constexpr int kExtraSmemBytes = 0;
+    alignas(64) CUtensorMap tmap;                                  // dims {C, W, H, N} of the NHWC source
+    int H, W, tiles_x, tiles_y;
+    // interface stubs (the patch path has its own producer loop)
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
+    __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
+    __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
+};
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+                 : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across producer warp groups
 // Two MMA issuer warps alternate k-blocks (tcgen05.mma issue blocks the issuing thread, so one issuer leaves the tensor
@@ -239,16 +270,21 @@ struct TsCfg {
 };
 
 template <class AP, int BN, int NPASS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float* __restrict__ wblob, TileSched ts, int M, int sb, EpiStd epi,
-                                                              int dbg, long long* trace) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_constant__ AP ap_param, const float* __restrict__ wblob, TileSched ts,
+                                                              int M, int sb, int ps, EpiStd epi, int dbg, long long* trace) {
     using Cfg = TsCfg<BN, NPASS>;
     constexpr int SA = Cfg::SA;
+    constexpr bool kPatch = AP::kPatch;
+    // the gather producers keep per-thread state in their AP (private copy); the patch AP holds the TMA descriptor,
+    // which must stay in param space
+    typename std::conditional<kPatch, const AP&, AP>::type ap = ap_param;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     unsigned char* smem = smem_raw + pad;
-    const uint32_t sbase = raw_addr + pad;
-    // layout: [sb x B_STAGE] [barriers + tmem slot: 512 B] [AP extra]
+    // layout: [patch ring: ps x TP_STAGE_BYTES (patch producer only)] [sb x B_STAGE] [barriers + tmem slot: 512 B] [AP extra]
+    const uint32_t patch_bytes = kPatch ? (uint32_t)ps * TP_STAGE_BYTES : 0u;
+    const uint32_t sbase = raw_addr + pad + patch_bytes;  // weight ring
     const uint32_t bar_base = sbase + (uint32_t)sb * Cfg::B_STAGE;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -256,8 +292,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     auto b_empty = [&](int s) { return bar_base + 8u * (24 + s); };
     auto acc_full = [&](int b) { return bar_base + 8u * (32 + b); };
     auto acc_empty = [&](int b) { return bar_base + 8u * (34 + b); };
+    auto p_full = [&](int s) { return bar_base + 8u * (40 + s); };
+    auto p_empty = [&](int s) { return bar_base + 8u * (44 + s); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
-    unsigned char* ap_common = smem + (size_t)sb * Cfg::B_STAGE + 512;     // per-warp transpose stages + row tables
+    unsigned char* ap_common = smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 512;     // per-warp transpose stages + row tables
     unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -272,6 +310,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             mbar_init(acc_full(b), TS_ISSUERS);           // one commit (or plain arrive) per issuer warp
             mbar_init(acc_empty(b), TC_EWARPS);
         }
+        for (int s = 0; s < TP_MAX_STAGES; ++s) {
+            mbar_init(p_full(s), 1);
+            mbar_init(p_empty(s), TC_PWARPS);
+        }
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -279,11 +321,87 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (size_t)sb * Cfg::B_STAGE + 8 * 38);
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 8 * 38);
     const int tiles_mn = ts.m_tiles * ts.n_tiles;
 
     if (warp < TC_PWARPS) {
         // ===================== A producers: warp = (TMEM lane quadrant, k-group) =====================
+        if constexpr (kPatch) {
+            // ----- patch producer: thread = output pixel (ry, rx) of the 16x8 patch, operands from the TMA-filled halo patch
+            const int quad = warp & 3, grp = warp >> 2;
+            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+            const int r = quad * 32 + lane, ry = r >> 4, rx = r & 15;
+            int gk0 = 0, gc0 = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int z = t / tiles_mn;
+                const int kb0 = z * ts.kb_per_split;
+                const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;      // whole channel blocks: multiple of 9
+                int last_c = -1;
+                const float* pbase = nullptr;
+                int i = (grp - (gk0 % TS_KGROUPS) + TS_KGROUPS) % TS_KGROUPS;
+                for (; i < nkb; i += TS_KGROUPS) {
+                    const int c = i / 9, tap = i - c * 9;
+                    if (tid == grp * 128) TC_TRACE(1, gk0 + i, 0);
+                    if (c != last_c) {
+                        if (last_c >= 0) {                 // done with the previous channel block's patch
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
+                        }
+                        const int gc = gc0 + c;
+                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u);
+                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * TP_STAGE_BYTES);
+                        last_c = c;
+                    }
+                    const int gk = gk0 + i;
+                    const int sa = gk % SA;
+                    const uint32_t pa = (uint32_t)(gk / SA) & 1u;
+                    const uint32_t acol = tmem_base + lane_addr + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const int idx = (ry + ky) * TP_HW + rx + kx;
+                    const float* prow = pbase + idx * 32;
+                    const int sw = idx & 7;
+                    float4 x[8];
+                    if (!(dbg & 2)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow + ((q ^ sw) << 2));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (tid == grp * 128) TC_TRACE(1, gk, 1);
+                    mbar_wait(a_empty(sa), pa ^ 1u);
+                    tc_fence_after();
+                    if (tid == grp * 128) TC_TRACE(1, gk, 2);
+                    if (!(dbg & 4)) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float v[8] = {x[2 * q].x, x[2 * q].y, x[2 * q].z, x[2 * q].w, x[2 * q + 1].x, x[2 * q + 1].y, x[2 * q + 1].z, x[2 * q + 1].w};
+                            float hi[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hi[j] = tf32_rna(v[j]);
+                            tmem_st8(acol + (uint32_t)(q * 8), hi);
+                            if (NPASS == 3) {
+                                float lo[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) lo[j] = v[j] - hi[j];
+                                tmem_st8(acol + 32u + (uint32_t)(q * 8), lo);
+                            }
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full(sa));
+                    if (tid == grp * 128) TC_TRACE(1, gk, 3);
+                }
+                if (last_c >= 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
+                }
+                gk0 += nkb;
+                gc0 += nkb / 9;
+            }
+        } else {
         const int quad = warp & 3, grp = warp >> 2;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         float* stage = reinterpret_cast<float*>(ap_common + (size_t)warp * TS_WARP_SMEM);
@@ -336,6 +454,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             }
             gk0 += nkb;
         }
+        }  // !kPatch
     } else if (warp < TC_MMA_WARP) {
         // ===================== epilogue warps =====================
         const int ewarp = warp - TC_PWARPS;
@@ -351,8 +470,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
             // issuer 1's accumulator holds a partial sum only when the tile has >= 2 k-blocks
-            if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), nullptr, ewarp, lane, m0, M, ntile, z,
-                                                  (TS_ISSUERS > 1 && nkb > 1) ? (uint32_t)BN : 0u);
+            const uint32_t acc2 = (TS_ISSUERS > 1 && nkb > 1) ? (uint32_t)BN : 0u;
+            if constexpr (kPatch) {
+                const int mt = mn / ts.n_tiles, per_img = ap.tiles_x * ap.tiles_y;
+                const int n = mt / per_img, tr = mt - n * per_img;
+                const int r = ewarp * 32 + lane;
+                const int y = (tr / ap.tiles_x) * TP_PH + (r >> 4), x = (tr % ap.tiles_x) * TP_PW + (r & 15);
+                if (!(dbg & 16)) epi.template run_p<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), ewarp, (n * ap.H + y) * ap.W + x, y < ap.H && x < ap.W, M, ntile, z, acc2);
+            } else {
+                if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), nullptr, ewarp, lane, m0, M, ntile, z, acc2);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(b));
@@ -440,6 +567,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
                 if (++s_b == sb) { s_b = 0; ph_b ^= 1u; }
             }
         }
+    } else if (warp == TC_AUX_WARP + 1) {
+        // ===================== halo-patch TMA loader (patch producer only) =====================
+        if constexpr (kPatch) {
+            int gc = 0;
+            const int per_img = ap.tiles_x * ap.tiles_y;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int mt = mn / ts.n_tiles;
+                const int n = mt / per_img, tr = mt - n * per_img;
+                const int y0 = (tr / ap.tiles_x) * TP_PH - 1, x0 = (tr % ap.tiles_x) * TP_PW - 1;
+                const int kb0 = z * ts.kb_per_split;
+                const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
+                const int c0 = kb0 / 9, nch = nkb / 9;
+                for (int c = 0; c < nch; ++c, ++gc) {
+                    const int s = gc % ps;
+                    mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
+                        tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
     }
     __syncthreads();
     if (warp == TC_AUX_WARP) {
@@ -449,13 +600,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(AP ap, const float
 }
 
 template <class AP, int BN, int NPASS>
-static int ts_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st) {
+static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st, int m_tiles_override = 0) {
     using Cfg = TsCfg<BN, NPASS>;
-    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_COMMON_SMEM + AP::kExtraSmemBytes;
+    constexpr int ps = AP::kPatch ? TP_MAX_STAGES : 0;
+    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + (AP::kPatch ? ps * TP_STAGE_BYTES : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
+    if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, 9) * 9;      // whole channel blocks per split
     ts.splits = ceil_div(nkb, ts.kb_per_split);
-    ts.m_tiles = ceil_div(M, TC_BM);
+    ts.m_tiles = m_tiles_override > 0 ? m_tiles_override : ceil_div(M, TC_BM);
     ts.n_tiles = n_tiles;
     ts.nkb_total = nkb;
     ts.total = ts.m_tiles * ts.n_tiles * ts.splits;
@@ -476,7 +629,7 @@ static int ts_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
     long long* trace = nullptr;
     if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
-    tc_ts_kernel<AP, BN, NPASS><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, sb, epi, dbg, trace);
+    tc_ts_kernel<AP, BN, NPASS><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, sb, ps, epi, dbg, trace);
     DEFT_CHECK_LAUNCH("tc_ts_kernel");
     return DEFT_OK;
 }

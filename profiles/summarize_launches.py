@@ -12,7 +12,7 @@ import sys
 
 def short(n):
     n = n.replace("void ", "").replace("deft::", "")
-    for eng in ("igemm_simt_kernel", "tc_igemm_kernel"):
+    for eng in ("igemm_simt_kernel", "tc_igemm_kernel", "tc_ts_kernel"):
         if eng in n:
             ap = "Dcn" if "DcnAP" in n else ("Pair" if "PairAP" in n else "Conv")
             tail = n.split("AP, ")[1].split(">")[0] if "AP, " in n else "?"

@@ -51,7 +51,10 @@ def test_layout_roundtrip(dev):
 @pytest.mark.parametrize("flags", ENGINES)
 @pytest.mark.parametrize("cin,cout,k,stride,hw", [(16, 16, 3, 1, (20, 28)), (16, 32, 3, 2, (20, 28)), (32, 64, 3, 2, (18, 22)),
                                                   (64, 64, 3, 1, (17, 19)), (128, 128, 3, 1, (9, 12)), (64, 128, 1, 1, (11, 13)),
-                                                  (256, 256, 3, 1, (6, 8)), (512, 512, 3, 1, (3, 4))])
+                                                  (256, 256, 3, 1, (6, 8)), (512, 512, 3, 1, (3, 4)),
+                                                  # 16x8-patch (TMA halo) producer: exact / ragged tilings, split-K, narrow N
+                                                  (64, 64, 3, 1, (30, 62)), (128, 64, 3, 1, (16, 32)), (256, 128, 3, 1, (30, 62)),
+                                                  (64, 32, 3, 1, (32, 48))])
 def test_conv_bn_act(dev, cin, cout, k, stride, hw, flags):
     from deft_b200 import ops, packing
     sp = {}
