@@ -56,16 +56,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must trap, never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug must trap, never hang the GPU.  After ~0.5 s every stuck warp reports where it waits
+// (site / aux are caller-defined: which barrier of the protocol, which k-block or tile), after ~1.5 s the kernel traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int aux = 0) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
+    bool reported = false;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("deft tc_engine: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x, bar, parity);
-            __trap();
+        const long long dt = clock64() - t0;
+        if (dt > 1000000000LL && !reported) {
+            reported = true;
+            if ((threadIdx.x & 31) == 0)
+                printf("deft tc_engine: mbarrier stall block %d warp %d site %d aux %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, site, aux, bar, parity);
         }
+        if (dt > 3000000000LL) __trap();
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -923,7 +927,7 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
 template <class AP>
 static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                        size_t scratch_bytes, cudaStream_t st) {
-    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0 || K % TC_BK != 0) return DEFT_EINVAL;
+    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0 || K % TC_BK != 0 || ldw > TS_SS_MAXC) return DEFT_EINVAL;
     const int nkb = K / TC_BK, nt = ldw / bn;
     int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
     if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
@@ -988,7 +992,7 @@ static bool patch_eligible(const ConvAP& ap) {
 }
 static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                           size_t scratch_bytes, cudaStream_t st) {
-    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0) return DEFT_EINVAL;
+    if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0 || ldw > TS_SS_MAXC) return DEFT_EINVAL;
     TmapEncodeFn enc = tmap_encoder();
     if (enc == nullptr) return DEFT_EINVAL;
     TsPatchAP t{};

@@ -269,6 +269,93 @@ struct TsCfg {
     static constexpr int B_STAGE = NPASS == 3 ? 2 * B_TILE : B_TILE;
 };
 
+// Accumulator tile -> output, 32 (or BN) columns at a time.  tcgen05.ld hands every lane one accumulator ROW; storing
+// rows from there touches 32 different lines per store instruction and fills only half of every 32-byte sector.  So
+// each epilogue warp parks its 32 x LW block in a padded smem stage and re-reads it with LW/4 lanes per row: every
+// global access (output, residual, split-K partial) is then 128 contiguous bytes per row.  Scale / shift sit in smem.
+constexpr int TS_EPI_LD = 36;                                       // floats per staged row (32 + 4 pad)
+constexpr int TS_SS_MAXC = 512;                                     // widest layer whose scale/shift are staged in smem
+constexpr int TS_EPI_SMEM = TC_EWARPS * 32 * TS_EPI_LD * 4 + 2 * TS_SS_MAXC * 4;    // transpose stages + scale + shift
+struct TsRowMap {                                                   // accumulator row (0..127) of this tile -> output pixel
+    int base, H, W, y0, x0, M;                                      // patch: y0/x0/H/W, base = n*H*W; linear: base = m0, W = 0
+    __device__ __forceinline__ int pixel(int row, bool& valid) const {
+        if (W == 0) { const int p = base + row; valid = p < M; return p; }
+        const int y = y0 + (row >> 4), x = x0 + (row & 15);
+        valid = y < H && x < W;
+        return base + y * W + x;
+    }
+};
+template <int BN>
+__device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc, uint32_t acc2_cols, int ewarp, int lane, const TsRowMap& rm, int ntile,
+                                            int z, float* stage, const float* ss) {
+    const Epilogue& e = epi.e;
+    constexpr int LW = BN >= 32 ? 32 : BN;
+    constexpr int LPR = LW / 4;                                     // lanes per row in the coalesced mapping
+    constexpr int RPI = 32 / LPR;                                   // rows per instruction
+    const uint32_t lane_addr = (uint32_t)(ewarp * 32) << 16;
+    const int cq = (lane % LPR) * 4, rsub = lane / LPR;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += LW) {
+        __syncwarp();                                               // the previous block's readers are done with the stage
+        constexpr int LH = LW >= 16 ? 16 : LW;                      // 16 columns at a time keeps the register count down
+#pragma unroll
+        for (int h = 0; h < LW; h += LH) {
+            float v[LH];
+            tmem_ld<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), v);
+            if (acc2_cols) {                                        // the second issuer's accumulator, added in a fixed order
+                float v2[LH];
+                tmem_ld<LH>(tmem_acc + acc2_cols + lane_addr + (uint32_t)(c + h), v2);
+#pragma unroll
+                for (int j = 0; j < LH; ++j) v[j] += v2[j];
+            }
+#pragma unroll
+            for (int q = 0; q < LH / 4; ++q)
+                *reinterpret_cast<float4*>(stage + lane * TS_EPI_LD + h + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
+        __syncwarp();
+        const int col = ntile * BN + c + cq;                        // this lane's 4 output channels
+        if (epi.partial != nullptr) {                               // split-K: raw partial sums, reduced by splitk_reduce_kernel
+#pragma unroll
+            for (int j = 0; j < 32 / RPI; ++j) {
+                const int row = rsub + RPI * j;
+                bool valid;
+                const int p = rm.pixel(ewarp * 32 + row, valid);
+                if (valid) *reinterpret_cast<float4*>(epi.partial + ((size_t)z * rm.M + p) * epi.ldp + col) = *reinterpret_cast<const float4*>(stage + row * TS_EPI_LD + cq);
+            }
+            continue;
+        }
+        const bool col_ok = col < e.Cout;
+        const float4 sc = *reinterpret_cast<const float4*>(ss + (col_ok ? col : 0));
+        const float4 sh = *reinterpret_cast<const float4*>(ss + TS_SS_MAXC + (col_ok ? col : 0));
+        constexpr int NJ = 32 / RPI, JB = NJ >= 2 ? 2 : NJ;        // rows of this lane, JB at a time: loads first, then the stores
+#pragma unroll
+        for (int j0 = 0; j0 < NJ; j0 += JB) {
+            float4 a[JB], rr[JB];
+            int pp[JB];
+            bool ok[JB];
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                const int row = rsub + RPI * (j0 + j);
+                a[j] = *reinterpret_cast<const float4*>(stage + row * TS_EPI_LD + cq);
+                bool valid;
+                pp[j] = rm.pixel(ewarp * 32 + row, valid);
+                ok[j] = valid && col_ok;
+                rr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[j] && e.residual) rr[j] = ldg4(e.residual + (size_t)pp[j] * e.res_pitch + col);
+            }
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                if (!ok[j]) continue;
+                float4 o;
+                o.x = a[j].x * sc.x + sh.x + rr[j].x; o.y = a[j].y * sc.y + sh.y + rr[j].y;
+                o.z = a[j].z * sc.z + sh.z + rr[j].z; o.w = a[j].w * sc.w + sh.w + rr[j].w;
+                if (e.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(e.out + (size_t)pp[j] * e.out_pitch + col) = o;
+            }
+        }
+    }
+}
+
 template <class AP, int BN, int NPASS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_constant__ AP ap_param, const float* __restrict__ wblob, TileSched ts,
                                                               int M, int sb, int ps, EpiStd epi, int dbg, long long* trace) {
@@ -282,7 +369,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
     unsigned char* smem = smem_raw + pad;
-    // layout: [patch ring: ps x TP_STAGE_BYTES (patch producer only)] [sb x B_STAGE] [barriers + tmem slot: 512 B] [AP extra]
+    // layout: [patch ring: ps x TP_STAGE_BYTES (patch producer only)] [sb x B_STAGE] [barriers + tmem slot: 512 B] [epilogue stages]
+    //         [producer stages (gather producers only)] [AP extra]
     const uint32_t patch_bytes = kPatch ? (uint32_t)ps * TP_STAGE_BYTES : 0u;
     const uint32_t sbase = raw_addr + pad + patch_bytes;  // weight ring
     const uint32_t bar_base = sbase + (uint32_t)sb * Cfg::B_STAGE;
@@ -295,7 +383,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     auto p_full = [&](int s) { return bar_base + 8u * (40 + s); };
     auto p_empty = [&](int s) { return bar_base + 8u * (44 + s); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
-    unsigned char* ap_common = smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 512;     // per-warp transpose stages + row tables
+    unsigned char* epi_stage = smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 512;     // epilogue warps' transpose stages, scale, shift
+    unsigned char* ap_common = epi_stage + TS_EPI_SMEM;                                  // producer warps' transpose stages + row tables
     unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                             if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
                         }
                         const int gc = gc0 + c;
-                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u);
+                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc);
                         pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * TP_STAGE_BYTES);
                         last_c = c;
                     }
@@ -369,7 +458,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                         for (int q = 0; q < 8; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (tid == grp * 128) TC_TRACE(1, gk, 1);
-                    mbar_wait(a_empty(sa), pa ^ 1u);
+                    mbar_wait(a_empty(sa), pa ^ 1u, 2, gk);
+                    __syncwarp();                              // converged before the .aligned tcgen05.st
                     tc_fence_after();
                     if (tid == grp * 128) TC_TRACE(1, gk, 2);
                     if (!(dbg & 4)) {
@@ -425,7 +515,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 if (!(dbg & 2)) ap.fill(kb0 + i, quad, lane, meta, stage);     // coalesced loads -> private smem stage
                 __syncwarp();
                 if (tid == grp * 128) TC_TRACE(1, gk, 1);
-                mbar_wait(a_empty(sa), pa ^ 1u);
+                mbar_wait(a_empty(sa), pa ^ 1u, 2, gk);
+                    __syncwarp();                              // converged before the .aligned tcgen05.st
                 tc_fence_after();
                 if (tid == grp * 128) TC_TRACE(1, gk, 2);
                 if (!(dbg & 4)) {
@@ -458,6 +549,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     } else if (warp < TC_MMA_WARP) {
         // ===================== epilogue warps =====================
         const int ewarp = warp - TC_PWARPS;
+        const int etid = ewarp * 32 + lane;
+        // scale / shift of every output channel, once per CTA (defaults 1 / 0; columns >= Cout are never stored)
+        float* ss = reinterpret_cast<float*>(epi_stage) + TC_EWARPS * 32 * TS_EPI_LD;
+        for (int i = etid; i < TS_SS_MAXC; i += TC_EWARPS * 32) {
+            ss[i] = (epi.e.scale != nullptr && i < epi.e.Cout) ? __ldg(epi.e.scale + i) : 1.f;
+            ss[TS_SS_MAXC + i] = (epi.e.shift != nullptr && i < epi.e.Cout) ? __ldg(epi.e.shift + i) : 0.f;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
         int iter = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
@@ -466,20 +565,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 0);
-            mbar_wait(acc_full(b), (uint32_t)(iter / Cfg::NBUF) & 1u);
+            mbar_wait(acc_full(b), (uint32_t)(iter / Cfg::NBUF) & 1u, 3, iter);
+            __syncwarp();                                  // converged before the .aligned tcgen05.ld
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
             // issuer 1's accumulator holds a partial sum only when the tile has >= 2 k-blocks
             const uint32_t acc2 = (TS_ISSUERS > 1 && nkb > 1) ? (uint32_t)BN : 0u;
+            TsRowMap rm{};
+            rm.M = M;
             if constexpr (kPatch) {
                 const int mt = mn / ts.n_tiles, per_img = ap.tiles_x * ap.tiles_y;
                 const int n = mt / per_img, tr = mt - n * per_img;
-                const int r = ewarp * 32 + lane;
-                const int y = (tr / ap.tiles_x) * TP_PH + (r >> 4), x = (tr % ap.tiles_x) * TP_PW + (r & 15);
-                if (!(dbg & 16)) epi.template run_p<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), ewarp, (n * ap.H + y) * ap.W + x, y < ap.H && x < ap.W, M, ntile, z, acc2);
+                rm.base = n * ap.H * ap.W; rm.H = ap.H; rm.W = ap.W;
+                rm.y0 = (tr / ap.tiles_x) * TP_PH; rm.x0 = (tr % ap.tiles_x) * TP_PW;
             } else {
-                if (!(dbg & 16)) epi.template run<BN>(tmem_base + (uint32_t)(b * TS_ISSUERS * BN), nullptr, ewarp, lane, m0, M, ntile, z, acc2);
+                rm.base = m0;                              // W = 0: rows are consecutive pixels
             }
+            if (!(dbg & 16))
+                ts_epilogue<BN>(epi, tmem_base + (uint32_t)(b * TS_ISSUERS * BN), acc2, ewarp, lane, rm, ntile, z,
+                                reinterpret_cast<float*>(epi_stage) + ewarp * 32 * TS_EPI_LD, ss);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(b));
@@ -498,7 +602,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             const int b = iter % Cfg::NBUF;
             const uint32_t tile_par = (uint32_t)(iter / Cfg::NBUF) & 1u;
-            mbar_wait(acc_empty(b), tile_par ^ 1u);
+            mbar_wait(acc_empty(b), tile_par ^ 1u, 4, iter);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)((b * TS_ISSUERS + w) * BN);
             for (int i = w; i < nkb; i += TS_ISSUERS) {
@@ -508,9 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int s_b = gk % sb;
                 const uint32_t ph_b = (uint32_t)(gk / sb) & 1u;
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 0);
-                mbar_wait(a_full(sa), pa);
+                mbar_wait(a_full(sa), pa, 5, gk);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 1);
-                mbar_wait(b_full(s_b), ph_b);
+                mbar_wait(b_full(s_b), ph_b, 6, gk);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 2);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
@@ -553,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * ts.nkb_total + kb0) * (2 * Cfg::B_TILE);
             for (int i = 0; i < nkb; ++i, ++gk) {
                 if (lane == 0) TC_TRACE(2, gk, 0);
-                mbar_wait(b_empty(s_b), ph_b ^ 1u);
+                mbar_wait(b_empty(s_b), ph_b ^ 1u, 7, gk);
                 if (lane == 0) TC_TRACE(2, gk, 1);
                 const uint32_t dst = sbase + (uint32_t)s_b * Cfg::B_STAGE;
                 if (elect_one_sync()) {
@@ -582,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int c0 = kb0 / 9, nch = nkb / 9;
                 for (int c = 0; c < nch; ++c, ++gc) {
                     const int s = gc % ps;
-                    mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u);
+                    mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
                         tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
@@ -603,7 +707,7 @@ template <class AP, int BN, int NPASS>
 static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st, int m_tiles_override = 0) {
     using Cfg = TsCfg<BN, NPASS>;
     constexpr int ps = AP::kPatch ? TP_MAX_STAGES : 0;
-    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + (AP::kPatch ? ps * TP_STAGE_BYTES : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
+    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * TP_STAGE_BYTES : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
     if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, 9) * 9;      // whole channel blocks per split

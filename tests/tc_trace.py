@@ -27,7 +27,7 @@ t0 = int(t[t > 0].min())
 names = ["MMA: loop_top  full_a_ok  full_b_ok  committed", "PROD: top  issued  empty_ok  arrived", "BCOPY: top  empty_ok", "EPI: top  acc_full_ok  done"]
 for role in range(4):
     print(names[role])
-    n = 44 if role < 3 else 4
+    n = 44 if role < 3 else 24
     for i in range(n):
         row = t[role, i]
         if int(row.max()) == 0:
