@@ -26,6 +26,18 @@ METRIC = "frames/sec @1088x608, 100 dets x 500 tracks"
 WORKLOAD = "C2 MOT17-shape 1088x608 stream, DLA-34+DCNv2, K=100 dets, 5x100 track-memory affinity"
 
 
+def ncu_traffic():
+    """dram__bytes_read+write per deft_dcnv2_forward launch from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1_dcn_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return {"traffic": t["dram_bytes_per_launch_avg"], "traffic_source": "profiles/r1_dcn_ncu_traffic.json (ncu --set full, gather-GEMM kernel; "
+                "outputs stay in L2 under ncu's replay, so this is the cold read side)"}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -219,7 +231,8 @@ def gpu_arm(args, rank, local_rank, world):
                 "roofline": {"bound": "hbm", "kernel": "deft_dcnv2_forward (offset/mask conv + fused gather-GEMM), 16 layers/frame",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_frame": DCN_BYTES_PER_FRAME, "dcn_ms_per_frame": dcn_ms, "dcn_layers": n_dcn,
-                             "traffic": None}}
+                             "algorithmic_bytes_per_launch": DCN_BYTES_PER_FRAME / max(n_dcn, 1), "launch_ms_avg": dcn_ms / max(n_dcn, 1),
+                             **ncu_traffic()}}
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
             r = run_cpu(2, 0, budget_s=40.0, state_dict=sd)

@@ -1,20 +1,27 @@
 // tcgen05 (5th-gen tensor core) implicit-GEMM engine for sm_100a.
 //
-//   D[128 px, BN couts] (fp32, TMEM)  +=  A[128 x 32] (smem, K-major, SWIZZLE_128B)  x  B[BN x 32] (smem, K-major)
+//   D[128 px, BN couts] (fp32, TMEM)  +=  A[128 x 32] (tf32)  x  B[BN x 32] (smem, K-major, SWIZZLE_128B)
 //
-// * A is never materialised in HBM: 8 producer warps build each 128x32 tile on the fly (im2col over NHWC
-//   sources, the DCNv2 bilinear gather, or the affinity pair expansion) and write it straight into the UMMA
-//   canonical layout.  Global loads are software-pipelined in registers (issue for k-block kb+D while kb is
-//   converted/stored), so the mainloop runs at the tensor pipe's pace, not at L2 latency.
-// * B (weights) is pre-packed by tc_pack_weights_kernel as ready-made swizzled smem tile images, streamed in
-//   by one elected thread with cp.async.bulk (TMA bulk copy, mbarrier complete_tx).
-// * fp32 parity: 3xTF32 error compensation -- x = hi + lo (hi = rna_tf32(x)), D += hi*hi + lo*hi + hi*lo, three
+// Two persistent kernels (grid <= 148, one CTA per SM, tiles strided over CTAs) share the PTX wrappers, the weight
+// packer and the dispatch in this file:
+//   tc_ts_kernel (tc_ts.cuh)   N tile <= 128: A goes through TMEM (TS-mode UMMA).  16 producer warps split every
+//                              128x32 A block into tf32 hi + lo and tcgen05.st it; the operand source is either a
+//                              TMA-loaded 18x10 halo patch in smem (3x3/s1 convs: TsPatchAP) or coalesced gathers
+//                              transposed through a per-warp smem stage (1x1 / strided convs, the DCNv2 bilinear
+//                              gather, the affinity pair expansion).  Two MMA issuer warps with private accumulators,
+//                              4 epilogue warps (coalesced stores through an smem transpose), 1 weight-copy warp,
+//                              1 patch-TMA warp.
+//   tc_igemm_kernel (below)    both operands in smem (SS-mode).  Kept for the fused CenterNet heads (N tile = 256:
+//                              one head's hidden layer never leaves the SM) and as the DEFT_TC_TS=0 reference path.
+// * A is never materialised in HBM.
+// * B (weights) is pre-packed by tc_pack_weights_kernel as ready-made swizzled smem tile images (hi and lo), streamed
+//   in by one elected thread with cp.async.bulk (TMA bulk copy, mbarrier complete_tx).
+// * fp32 parity: 3xTF32 error compensation -- x = hi + lo (hi = rna_tf32(x)), D += lo*hi + hi*lo + hi*hi, three
 //   kind::tf32 MMAs per k-step into the same TMEM accumulator.  DEFT_FLAG_TF32X1 issues only hi*hi.
-// * Small-M layers (DLA levels 4/5 at 1/16, 1/32 resolution) are split along K over blockIdx.z; partials go
-//   to caller scratch and a deterministic reduce kernel applies the epilogue (no atomics).
-// * Warp roles: warps 0-7 A producers then epilogue (tcgen05.ld -> epilogue functor), warp 8 lane 0 MMA
-//   issuer, warp 9 TMEM allocator + lane 0 weight-tile bulk copies.  mbarrier ring of S stages:
-//   full_a (256 producer arrivals), full_b (tx bytes), empty (tcgen05.commit).
+// * Small-M layers (DLA levels 4/5 at 1/16, 1/32 resolution) are split along K; partials go to caller scratch and
+//   a deterministic reduce kernel applies the epilogue (no atomics).  A stream-K variant was measured and dropped
+//   (profiles/r1_streamk_experiment.md).
+// * Every mbarrier wait is bounded (mbar_wait): a protocol bug reports its site and traps, it never hangs the GPU.
 #include <cuda.h>
 #include <type_traits>
 #include "tc_engine.cuh"

@@ -6,10 +6,12 @@
 //   * producer thread = one accumulator row.  16 producer warps = 4 TMEM lane quadrants x 4 k-block groups; a warp
 //     loads its 32 rows' 128 contiguous bytes per k-block (im2col tap / deformable gather / pair expansion), splits
 //     them into tf32 hi + lo and writes them with tcgen05.st straight into TMEM columns (a ring of SA A-stages);
-//   * the MMA warp issues tcgen05.mma with A from TMEM and only B (weights, bulk-copied) from shared memory;
-//   * no generic->async proxy fence, no MEMBAR, no swizzle arithmetic, and shared memory holds only weights.
-// Everything else (persistent tile loop, double-buffered accumulators, dedicated epilogue warps, 3xTF32 split,
-// split-K partials) is as in tc_igemm_kernel.
+//   * two MMA warps issue tcgen05.mma with A from TMEM and only B (weights, bulk-copied) from shared memory; they
+//     alternate k-blocks and own one accumulator each, which the epilogue adds in a fixed order (bit-deterministic);
+//   * no generic->async proxy fence, no MEMBAR, no swizzle arithmetic on the A side;
+//   * 3x3 / stride-1 convolutions take their operands from a TMA-loaded halo patch instead (TsPatchAP below);
+//   * the epilogue transposes through shared memory so every global access is 128 contiguous bytes per row.
+// Persistent tile loop, double-buffered accumulators, 3xTF32 split and split-K partials are as in tc_igemm_kernel.
 #pragma once
 
 namespace deft {
