@@ -1,5 +1,7 @@
 // Shared helpers for libdeft_b200.so (sm_100a only).
 #pragma once
+#include <utility>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -37,5 +39,34 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+
+// ---- programmatic dependent launch (PDL).  Every kernel on the frame path starts with DEFT_PDL_PROLOGUE(): wait until
+// the predecessor grid in the stream has completed and its writes are visible (griddepcontrol.wait, a no-op without the
+// launch attribute), then let the successor begin launching while this grid runs.  The wait is the FIRST statement,
+// before any early return, so a grid never completes before its predecessor -- ordering stays transitive.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define DEFT_PDL_PROLOGUE() do { deft::pdl_wait(); deft::pdl_launch_dependents(); } while (0)
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DEFT_PDL"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace deft

@@ -24,6 +24,7 @@ template <int COUT, int STRIDE, int PX>
 __global__ void __launch_bounds__(128) conv3x3_c16_kernel(const float* __restrict__ x, int x_pitch, int H, int W, int OH, int OW,
                                                           const float* __restrict__ wp, int ldw, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, float* __restrict__ out, int out_pitch, int relu) {
+    DEFT_PDL_PROLOGUE();
     using Cfg = C16Cfg<COUT, STRIDE, PX>;
     extern __shared__ __align__(16) float c16_smem[];
     float4* tile = reinterpret_cast<float4*>(c16_smem);                 // [4][IH][IW]
@@ -105,7 +106,7 @@ inline int launch_conv3x3_c16(const float* x, int x_pitch, int N, int H, int W, 
         attr_done = true;
     }
     dim3 grid(ceil_div(OW, Cfg::TW), ceil_div(OH, Cfg::TH), N);
-    conv3x3_c16_kernel<COUT, STRIDE, PX><<<grid, 128, Cfg::SMEM_BYTES, st>>>(x, x_pitch, H, W, OH, OW, wp, ldw, scale, shift, out, out_pitch, relu);
+    launch_pdl(conv3x3_c16_kernel<COUT, STRIDE, PX>, dim3(grid), dim3(128), Cfg::SMEM_BYTES, st, x, x_pitch, H, W, OH, OW, wp, ldw, scale, shift, out, out_pitch, relu);
     DEFT_CHECK_LAUNCH("conv3x3_c16");
     return DEFT_OK;
 }

@@ -31,6 +31,7 @@ __device__ __forceinline__ float afe_src_index(float g, int size, int align_corn
 }
 
 __global__ void __launch_bounds__(256) afe_corner_kernel(AfeArgs a, const float* __restrict__ centres, float* __restrict__ partial) {
+    DEFT_PDL_PROLOGUE();
     __shared__ __align__(16) float patch[AFE_DETS * 16 * AFE_CCHUNK];   // [det][4x4 pixel][channel]
     __shared__ int sx0[AFE_DETS], sy0[AFE_DETS];
     const int k = blockIdx.y, z = blockIdx.z, tid = threadIdx.x;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) afe_corner_kernel(AfeArgs a, const float*
 }
 
 __global__ void afe_blend_kernel(AfeArgs a, const float* __restrict__ centres, const float* __restrict__ partial, float* __restrict__ emb) {
+    DEFT_PDL_PROLOGUE();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.N * a.Cemb) return;
     const int n = idx / a.Cemb, e = idx - n * a.Cemb;
@@ -165,9 +167,9 @@ int deft_afe_extract(const float* const* maps, const int* pitch, const int* C, c
     a.align_corners = align_corners;
     a.N = N;
     float* partial = reinterpret_cast<float*>(ws);
-    afe_corner_kernel<<<dim3(ceil_div(N, AFE_DETS), DEFT_AFE_MAPS, AFE_MAXSPLIT), 256, 0, to_stream(s)>>>(a, centres, partial);
+    launch_pdl(afe_corner_kernel, dim3(ceil_div(N, AFE_DETS), DEFT_AFE_MAPS, AFE_MAXSPLIT), dim3(256), 0, to_stream(s), a, centres, partial);
     DEFT_CHECK_LAUNCH("afe_corner");
-    afe_blend_kernel<<<ceil_div(N * a.Cemb, 256), 256, 0, to_stream(s)>>>(a, centres, partial, emb);
+    launch_pdl(afe_blend_kernel, dim3(ceil_div(N * a.Cemb, 256)), dim3(256), 0, to_stream(s), a, centres, partial, emb);
     DEFT_CHECK_LAUNCH("afe_blend");
     return DEFT_OK;
 }

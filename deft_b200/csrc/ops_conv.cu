@@ -44,6 +44,7 @@ constexpr int STEM_TW = 64, STEM_TH = 16, STEM_LD = 72;   // tile row stride (fl
 __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ x, int H, int W,
                                                       const float* __restrict__ wp, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, float* __restrict__ out, int out_pitch) {
+    DEFT_PDL_PROLOGUE();
     __shared__ __align__(16) float tile[3][STEM_TH + 6][STEM_LD];
     __shared__ __align__(16) float ws[147 * 16];
     const int n = blockIdx.z;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool2x2_kernel(const float* __restrict__ in, int in_pitch, float* __restrict__ out, int out_pitch,
                                   int N, int H, int W, int C4) {
+    DEFT_PDL_PROLOGUE();
     const int OH = H / 2, OW = W / 2;
     size_t total = (size_t)N * OH * OW * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -134,6 +136,7 @@ __global__ void maxpool2x2_kernel(const float* __restrict__ in, int in_pitch, fl
 __global__ void upsample_add_kernel(const float* __restrict__ x, int x_pitch, const float* __restrict__ wp,
                                     const float* __restrict__ skip, int skip_pitch, float* __restrict__ out, int out_pitch,
                                     int N, int h, int w, int C, int f) {
+    DEFT_PDL_PROLOGUE();
     const int OH = h * f, OW = w * f, C4 = C / 4, k = 2 * f, pd = f / 2;
     size_t total = (size_t)N * OH * OW * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -302,7 +305,7 @@ int deft_stem_conv7x7(const float* x, int N, int H, int W, const float* w_packed
                       float* out, int out_pitch, deft_stream_t s) {
     DEFT_REQUIRE(x && w_packed && scale && shift && out && out_pitch >= 16 && out_pitch % 4 == 0, "stem: bad args");
     dim3 grid(ceil_div(W, STEM_TW), ceil_div(H, STEM_TH), N), block(256);
-    stem7x7_kernel<<<grid, block, 0, to_stream(s)>>>(x, H, W, w_packed, scale, shift, out, out_pitch);
+    launch_pdl(stem7x7_kernel, dim3(grid), dim3(block), 0, to_stream(s), x, H, W, w_packed, scale, shift, out, out_pitch);
     DEFT_CHECK_LAUNCH("stem7x7");
     return DEFT_OK;
 }
@@ -313,7 +316,7 @@ int deft_maxpool2x2(const float* in, int in_pitch, float* out, int out_pitch, in
     size_t total = (size_t)N * (H / 2) * (W / 2) * (C / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    maxpool2x2_kernel<<<blocks, 256, 0, to_stream(s)>>>(in, in_pitch, out, out_pitch, N, H, W, C / 4);
+    launch_pdl(maxpool2x2_kernel, dim3(blocks), dim3(256), 0, to_stream(s), in, in_pitch, out, out_pitch, N, H, W, C / 4);
     DEFT_CHECK_LAUNCH("maxpool2x2");
     return DEFT_OK;
 }
@@ -367,7 +370,7 @@ int deft_upsample_add(const float* x, int x_pitch, const float* w_packed, const 
     size_t total = (size_t)N * h * f * w * f * (C / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    upsample_add_kernel<<<blocks, 256, 0, to_stream(s)>>>(x, x_pitch, w_packed, skip, skip_pitch, out, out_pitch, N, h, w, C, f);
+    launch_pdl(upsample_add_kernel, dim3(blocks), dim3(256), 0, to_stream(s), x, x_pitch, w_packed, skip, skip_pitch, out, out_pitch, N, h, w, C, f);
     DEFT_CHECK_LAUNCH("upsample_add");
     return DEFT_OK;
 }

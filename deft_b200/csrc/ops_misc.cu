@@ -8,6 +8,7 @@ namespace deft {
 // ================================================================================================
 // a6: sigmoid_output
 __global__ void sigmoid_output_kernel(float* hm, size_t n_hm, float* dep, size_t n_dep, float depth_scale) {
+    DEFT_PDL_PROLOGUE();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t j = i; j < n_hm; j += stride) hm[j] = sigmoidf_(hm[j]);
@@ -62,6 +63,7 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n /* pow2 */) {
 constexpr int TOPK_CHUNK = 4096;
 __global__ void __launch_bounds__(1024) topk_chunk_kernel(const float* __restrict__ hm, int H, int W, int K, int nchunks,
                                                           unsigned long long* __restrict__ cand) {
+    DEFT_PDL_PROLOGUE();
     __shared__ unsigned long long keys[TOPK_CHUNK];
     const int HW = H * W;
     const size_t plane = (size_t)blockIdx.z * gridDim.y + blockIdx.y;
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(1024) topk_chunk_kernel(const float* __restric
 // Stage B: per (class, batch) merge of the chunk winners -> the per-class top-K of utils.py:92.
 __global__ void __launch_bounds__(1024) topk_class_merge_kernel(const unsigned long long* __restrict__ cand_chunk, int n, int Np, int K,
                                                                 unsigned long long* __restrict__ cand) {
+    DEFT_PDL_PROLOGUE();
     extern __shared__ unsigned long long mkeys[];
     const size_t plane = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     const unsigned long long* src = cand_chunk + plane * n;
@@ -101,6 +104,7 @@ struct DecodeArgs {
 
 // Second stage (utils.py:98-104) + gathers + box arithmetic (decode.py:113-183).  One block per image.
 __global__ void __launch_bounds__(1024) decode_merge_kernel(DecodeArgs a, int Np) {
+    DEFT_PDL_PROLOGUE();
     extern __shared__ unsigned long long skeys[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int CK = a.C * a.K, HW = a.H * a.W;
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(1024) decode_merge_kernel(DecodeArgs a, int Np
 
 __global__ void gather_feat_kernel(const float* __restrict__ feat, int C, int HW, const long long* __restrict__ inds, int K,
                                    float* __restrict__ out, int total) {
+    DEFT_PDL_PROLOGUE();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int c = i % C;
@@ -155,6 +160,7 @@ __global__ void gather_feat_kernel(const float* __restrict__ feat, int C, int HW
 }
 
 __global__ void boxes_to_centres_kernel(const float* __restrict__ b, int N, float W, float H, float* __restrict__ c) {
+    DEFT_PDL_PROLOGUE();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     // convert_detection: w = x2-x1; x1/=W; w/=W; c = 2*x1 + w - 1
@@ -166,6 +172,7 @@ __global__ void boxes_to_centres_kernel(const float* __restrict__ b, int N, floa
 // ================================================================================================
 // a8: affinity tail.  S[p] = relu(h4[p,:64] . w5 + b5); then the dual softmax.
 __global__ void affinity_final_kernel(const float* __restrict__ h4, const float* __restrict__ w5, float b5, float* __restrict__ S, int M) {
+    DEFT_PDL_PROLOGUE();
     int p = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);   // 8 lanes per pair
     int l = threadIdx.x & 7;
     float s = 0.f;
@@ -188,6 +195,7 @@ struct SoftmaxArgs {
 // One block per memory frame.  X = [[S (n x m), 0...; 0...], ones row/col] of size (P+1)^2 as in
 // AFE.py:123-134; rows/cols beyond n/m are exact zeros and enter the denominators analytically.
 __global__ void __launch_bounds__(256) affinity_softmax_kernel(const float* __restrict__ S, SoftmaxArgs a, float* __restrict__ out) {
+    DEFT_PDL_PROLOGUE();
     extern __shared__ float sm[];
     const int P = a.P, m = a.m, f = blockIdx.x, n = a.n[f];
     float* rmax = sm; float* rsum = sm + P; float* cmax = sm + 2 * P; float* csum = sm + 3 * P;
@@ -292,7 +300,7 @@ int deft_sigmoid_output(float* hm, size_t n_hm, float* dep, size_t n_dep, float 
     if (n == 0) return DEFT_OK;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    sigmoid_output_kernel<<<blocks, 256, 0, to_stream(s)>>>(hm, hm ? n_hm : 0, dep, dep ? n_dep : 0, depth_scale);
+    launch_pdl(sigmoid_output_kernel, dim3(blocks), dim3(256), 0, to_stream(s), hm, hm ? n_hm : 0, dep, dep ? n_dep : 0, depth_scale);
     DEFT_CHECK_LAUNCH("sigmoid_output");
     return DEFT_OK;
 }
@@ -321,7 +329,7 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
     unsigned long long* cand_chunk = reinterpret_cast<unsigned long long*>(ws);
     unsigned long long* cand = reinterpret_cast<unsigned long long*>(
         reinterpret_cast<char*>(ws) + align_up((size_t)B * C * nchunks * K * sizeof(unsigned long long), 256));
-    topk_chunk_kernel<<<dim3(nchunks, C, B), 1024, 0, to_stream(s)>>>(hm, H, W, K, nchunks, cand_chunk);
+    launch_pdl(topk_chunk_kernel, dim3(nchunks, C, B), dim3(1024), 0, to_stream(s), hm, H, W, K, nchunks, cand_chunk);
     DEFT_CHECK_LAUNCH("topk_chunk");
     static size_t attr_b = 48 * 1024, attr_c = 48 * 1024;
     size_t smem_b = (size_t)Mp * sizeof(unsigned long long);
@@ -329,7 +337,7 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
         cudaFuncSetAttribute(topk_class_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         attr_b = smem_b;
     }
-    topk_class_merge_kernel<<<dim3(C, B), 1024, smem_b, to_stream(s)>>>(cand_chunk, nchunks * K, Mp, K, cand);
+    launch_pdl(topk_class_merge_kernel, dim3(C, B), dim3(1024), smem_b, to_stream(s), cand_chunk, nchunks * K, Mp, K, cand);
     DEFT_CHECK_LAUNCH("topk_class_merge");
     DecodeArgs a{cand, reg, wh, ltrb_amodal, scores, (long long*)inds, clses, ys, xs, bboxes, bboxes_amodal, C, H, W, K};
     size_t smem = (size_t)Np * sizeof(unsigned long long);
@@ -337,7 +345,7 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
         cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_c = smem;
     }
-    decode_merge_kernel<<<B, 1024, smem, to_stream(s)>>>(a, Np);
+    launch_pdl(decode_merge_kernel, dim3(B), dim3(1024), smem, to_stream(s), a, Np);
     DEFT_CHECK_LAUNCH("decode_merge");
     return DEFT_OK;
 }
@@ -345,14 +353,14 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
 int deft_gather_feat(const float* feat, int B, int C, int HW, const int64_t* inds, int K, float* out, deft_stream_t s) {
     DEFT_REQUIRE(feat && inds && out && B > 0 && C > 0 && K > 0, "gather_feat: bad args");
     int total = B * K * C;
-    gather_feat_kernel<<<ceil_div(total, 256), 256, 0, to_stream(s)>>>(feat, C, HW, (const long long*)inds, K, out, total);
+    launch_pdl(gather_feat_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, to_stream(s), feat, C, HW, (const long long*)inds, K, out, total);
     DEFT_CHECK_LAUNCH("gather_feat");
     return DEFT_OK;
 }
 
 int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* centres, deft_stream_t s) {
     DEFT_REQUIRE(boxes && centres && N > 0 && W > 0 && H > 0, "boxes_to_centres: bad args");
-    boxes_to_centres_kernel<<<ceil_div(N, 128), 128, 0, to_stream(s)>>>(boxes, N, W, H, centres);
+    launch_pdl(boxes_to_centres_kernel, dim3(ceil_div(N, 128)), dim3(128), 0, to_stream(s), boxes, N, W, H, centres);
     DEFT_CHECK_LAUNCH("boxes_to_centres");
     return DEFT_OK;
 }
@@ -430,10 +438,10 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
     if (rc != DEFT_OK) return rc;
     if ((rc = plain_gemm(h2, 256, M, 256, w3, t3, bn[3], 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
     if ((rc = plain_gemm(h3, 128, M, 128, w4, t4, bn[4], 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
-    affinity_final_kernel<<<ceil_div(M, 32), 256, 0, st>>>(h4, w5, b5, S, M);
+    launch_pdl(affinity_final_kernel, dim3(ceil_div(M, 32)), dim3(256), 0, st, h4, w5, b5, S, M);
     DEFT_CHECK_LAUNCH("affinity_final");
     sa.m = m; sa.P = P;
-    affinity_softmax_kernel<<<F, 256, 4 * P * sizeof(float), st>>>(S, sa, out);
+    launch_pdl(affinity_softmax_kernel, dim3(F), dim3(256), 4 * P * sizeof(float), st, S, sa, out);
     DEFT_CHECK_LAUNCH("affinity_softmax");
     return DEFT_OK;
 }

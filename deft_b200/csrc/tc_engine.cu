@@ -567,6 +567,7 @@ template <class AP, int BN, int NPASS, class EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const float* __restrict__ wblob, TileSched ts, int M, int stages, EPI epi,
                                                                  int dbg, long long* trace) {
     // trace (DEFT_TC_TRACE, perf bring-up only): CTA 0 records clock64() at protocol points, [role][k-block < 96][4]
+    DEFT_PDL_PROLOGUE();
 #define TC_TRACE(role, idx, slot) do { if (trace != nullptr && blockIdx.x == 0 && (idx) < 96) trace[((role) * 96 + (idx)) * 4 + (slot)] = clock64(); } while (0)
     constexpr int B_TILE = BN * 128;                      // bytes of one B part (hi or lo)
     constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
@@ -774,6 +775,7 @@ namespace deft {
 
 // Deterministic split-K tail: out = epilogue(sum_z partial[z]).
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int ldp, Epilogue e) {
+    DEFT_PDL_PROLOGUE();
     const int c4 = e.Cout / 4;
     size_t total = (size_t)M * c4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -894,7 +896,7 @@ static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
     long long* trace = nullptr;
     if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
-    tc_igemm_kernel<AP, BN, NPASS, EPI><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, stages, epi, dbg, trace);
+    launch_pdl(tc_igemm_kernel<AP, BN, NPASS, EPI>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, stages, epi, dbg, trace);
     DEFT_CHECK_LAUNCH("tc_igemm_kernel");
     return DEFT_OK;
 }
@@ -926,7 +928,7 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     size_t total = (size_t)M * (ep.Cout / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
     DEFT_CHECK_LAUNCH("splitk_reduce");
     return DEFT_OK;
 }
@@ -958,7 +960,7 @@ static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     size_t total = (size_t)M * (ep.Cout / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
     DEFT_CHECK_LAUNCH("splitk_reduce");
     return DEFT_OK;
 }
@@ -1038,7 +1040,7 @@ static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, 
     size_t total = (size_t)M * (ep.Cout / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
-    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
     DEFT_CHECK_LAUNCH("splitk_reduce");
     return DEFT_OK;
 }

@@ -31,6 +31,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
+// Programmatic dependent launch (common.cuh): here only what reads or writes ACTIVATIONS waits for the predecessor
+// grid; barrier init, TMEM allocation, scale/shift staging and the weight ring start right away.  Every CTA has
+// producer and epilogue warps that wait, so a CTA never retires before the predecessor grid has completed.
 // ------------------------------------------------------------------------------------------------ producers
 // A producer warp owns 32 rows (one TMEM lane quadrant) and every 4th k-block.  Per k-block it
 //   1. fill(): loads the rows' 128 B with the COALESCED mapping (8 lanes x 16 B per row, 4 rows per LDG.128) -- the
@@ -414,9 +417,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 8 * 38);
     const int tiles_mn = ts.m_tiles * ts.n_tiles;
+    pdl_launch_dependents();                              // the next launch may take SMs as our CTAs retire
 
     if (warp < TC_PWARPS) {
         // ===================== A producers: warp = (TMEM lane quadrant, k-group) =====================
+        pdl_wait();                                       // activations (and the DCN offset map) come from the predecessor
         if constexpr (kPatch) {
             // ----- patch producer: thread = output pixel (ry, rx) of the 16x8 patch, operands from the TMA-filled halo patch
             const int quad = warp & 3, grp = warp >> 2;
@@ -559,6 +564,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             ss[TS_SS_MAXC + i] = (epi.e.shift != nullptr && i < epi.e.Cout) ? __ldg(epi.e.shift + i) : 0.f;
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
+        pdl_wait();                                       // residual reads, output / scratch writes
         int iter = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
@@ -676,6 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     } else if (warp == TC_AUX_WARP + 1) {
         // ===================== halo-patch TMA loader (patch producer only) =====================
         if constexpr (kPatch) {
+            pdl_wait();                                   // the TMA reads the predecessor's output
             int gc = 0;
             const int per_img = ap.tiles_x * ap.tiles_y;
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
@@ -735,7 +742,10 @@ static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tile
     long long* trace = nullptr;
     if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
-    tc_ts_kernel<AP, BN, NPASS><<<grid, TC_THREADS, smem, st>>>(ap, blob, ts, M, sb, ps, epi, dbg, trace);
+    if (launch_pdl(tc_ts_kernel<AP, BN, NPASS>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, sb, ps, epi, dbg, trace) != cudaSuccess) {
+        set_error("tc_ts_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return DEFT_ECUDA;
+    }
     DEFT_CHECK_LAUNCH("tc_ts_kernel");
     return DEFT_OK;
 }
