@@ -150,7 +150,7 @@ def gpu_arm(args, rank, local_rank, world):
     model = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt).eval()
     randomize_(model, seed=317 + rank)
     model = model.to(dev)
-    pipe = FramePipeline(model, opt, H, W, mem_frames=MEM_FRAMES, device=dev, use_cuda_graph=not args.no_graph)
+    pipe = FramePipeline(model, opt, H, W, mem_frames=MEM_FRAMES, device=dev, use_cuda_graph=not args.no_graph, depth=args.depth)
     g = torch.Generator(); g.manual_seed(1234 + rank)
     frames_host = [torch.randn((1, 3, H, W), generator=g).pin_memory() for _ in range(4)]    # distinct frames, pinned
     frames_dev = [f.to(dev) for f in frames_host]
@@ -160,45 +160,38 @@ def gpu_arm(args, rank, local_rank, world):
     for i in range(max(args.warmup, 3)):
         out_host = pipe.step(frames_host[i % 4], out_host)
     torch.cuda.synchronize(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(step_fn, flush_l2):
-        evs = []
+    def timed(step_fn):
+        """K back-to-back steps between one CUDA-event pair on the launching stream (the pipeline's second stream is
+        joined into it before the closing event), barrier + device synchronize on both sides, max over ranks.
+        No L2 flush: one frame touches ~1 GB of unique bytes (0.33 GB packed weights + tile images, 0.8 GB
+        activation arena, two arenas alternating) >> 126 MB L2, and the input frames rotate."""
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        if flush_l2:
-            for i in range(args.steps):
-                flush.zero_()                            # L2 flush between timed iterations (outside the event pair)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                step_fn(i)
-                e1.record()
-                evs.append((e0, e1))
-        else:                                            # one event pair around the K back-to-back steps (copies overlap compute)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(args.steps):
-                step_fn(i)
-            e1.record()
-            evs.append((e0, e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step_fn(i)
+        pipe.join()
+        e1.record()
         barrier()
         sampler.stop_flag = True
         sampler.join()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        ms = e0.elapsed_time(e1)
         _, ms_max = aggregate_throughput(float(args.steps), ms, device=dev)      # max over ranks of the device time
         return ms_max, sampler.summary()
 
     # (1) device-resident value: frames already in HBM
-    ms_dev, clocks = timed(lambda i: pipe.step_device(frames_dev[i % 4]), True)
+    ms_dev, clocks = timed(lambda i: pipe.step_device(frames_dev[i % 4]))
     # (2) end to end through the public API: pinned host frame in, host results out, every copy inside the timed
     #     region; each frame arrives cold from the host and a frame's 1.4 GB working set >> L2, so no extra flush
-    ms_e2e, clocks_e2e = timed(lambda i: pipe.step(frames_host[i % 4], out_host), False)
+    ms_e2e, clocks_e2e = timed(lambda i: pipe.step(frames_host[i % 4], out_host))
     h2d = frames_host[0].numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
@@ -222,7 +215,8 @@ def gpu_arm(args, rank, local_rank, world):
                 "dtype": "f32" if args.simt else ("tf32" if args.tf32x1 else "f32 (3xTF32 tensor-core where covered, fp32 SIMT elsewhere)"),
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "parallelism": f"stream-parallel x{world} (no collective)",
-                           "cuda_graph": not args.no_graph, "l2": "256 MB flush between timed iterations; per-frame working set ~1.4 GB >> 126 MB L2",
+                           "cuda_graph": not args.no_graph, "frame_pipelining": f"depth {pipe.depth} (dense part of frame t+1 over the decode/embedding/affinity tail of frame t)",
+                           "l2": "no flush: inputs larger than L2 (~1 GB of unique weights + activations per frame vs 126 MB L2, rotating input frames)",
                            "engine": "simt-fp32" if args.simt else "tcgen05"},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches * args.steps,
@@ -253,6 +247,7 @@ def main():
     ap.add_argument("--simt", action="store_true", help="fp32 SIMT anchor engine only")
     ap.add_argument("--tf32x1", action="store_true", help="single-pass TF32 (outside the parity budget)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--depth", type=int, default=2, choices=[1, 2], help="frame software-pipelining depth of the FramePipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -190,8 +190,10 @@ class DLASeg(nn.Module):
             fl |= ops.FLAG_TF32X1
         return fl
 
-    def plan_for(self, x):
-        key = (tuple(x.shape), x.device.index, self._flags())
+    def plan_for(self, x, slot=0):
+        """The frame plan (arena + launch list) for this input shape; `slot` > 0 asks for an additional, independent
+        arena (FramePipeline keeps two so that frame t+1's backbone can overlap frame t's decode/embedding tail)."""
+        key = (tuple(x.shape), x.device.index, self._flags(), slot)
         p = self._plans.get(key)
         if p is None:
             if self.training:

@@ -8,7 +8,8 @@ per frame between `images.to(device)` and the tracker's cost matrix (SURVEY.md s
       [-> LSTM motion step for T tracks when configured]
 
 and keeps the embedding memory (a ring of F frames x P rows) resident in HBM.  One instance per video
-stream / GPU; streams are independent (no collective), which is how the path shards across GPUs.
+stream / GPU; streams are independent (no collective), which is how the path shards across GPUs.  Within a
+stream, consecutive frames are software-pipelined two deep (dense part of frame t+1 over the tail of frame t).
 """
 from __future__ import annotations
 
@@ -25,7 +26,14 @@ KERNELS_PER_CALL = {  # CUDA kernels launched by each C-ABI entry point (for ben
 
 
 class FramePipeline:
-    def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True):
+    """depth=1: everything of a frame on the caller's stream.  depth=2 (default): software pipelining across the
+    frames of ONE video stream -- the dense part (DLASeg: backbone + heads) of frame t+1 runs on the caller's stream
+    while the small-grid tail of frame t (sigmoid, decode, embedding extractor, affinity, LSTM) runs on a second
+    stream over a second activation arena.  Results are identical to depth=1 (same kernels, same order per frame,
+    the embedding memory is only touched by the tail stream, in frame order); a frame's results are complete once the
+    device (or `tail_stream`) has been synchronised."""
+
+    def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True, depth=2):
         self.model, self.opt = model, opt
         self.device = device or next(model.parameters()).device
         self.H, self.W = height, width
@@ -33,15 +41,18 @@ class FramePipeline:
         self.P = opt.max_object
         if self.K > self.P:
             raise ValueError("K must be <= max_object (forward_stacker_features contract, AFE.py:110-122)")
+        if depth not in (1, 2):
+            raise ValueError("depth must be 1 or 2")
+        self.depth = depth
         self.F = mem_frames
         self.cemb = sum(model.AFE.selector_output_channel)
         self.lstm, self.T = lstm, lstm_tracks
         dev = self.device
-        self.x = torch.empty((1, 3, height, width), dtype=torch.float32, device=dev)           # device image slot
+        probe = torch.empty((1, 3, height, width), dtype=torch.float32, device=dev)
         self.memory = torch.zeros((self.F, self.P, self.cemb), dtype=torch.float32, device=dev)  # embedding ring
         self.counts = [self.K] * self.F          # live rows per memory frame (steady state: K detections/frame)
         self.head = 0
-        self.aff = torch.zeros((self.F, self.P, self.P + 1), dtype=torch.float32, device=dev)
+        self.aff = [torch.zeros((self.F, self.P, self.P + 1), dtype=torch.float32, device=dev) for _ in range(depth)]
         self.aff_ws = torch.empty(_lib.lib().deft_afe_affinity_workspace_bytes(self.F, self.P, self.cemb), dtype=torch.uint8, device=dev)
         self.ext_ws = torch.empty(_lib.lib().deft_afe_extract_workspace_bytes(self.K), dtype=torch.uint8, device=dev)
         self.dec_ws = None
@@ -50,17 +61,24 @@ class FramePipeline:
             self.lstm_h = torch.zeros((self.T, 128), device=dev)
             self.lstm_c = torch.zeros((self.T, 128), device=dev)
             self.lstm_x = torch.zeros((self.T, fin), device=dev)
-        self.plan = model.plan_for(self.x)
-        self.x = self.plan.x_in                   # the plan's static input slot: no extra device copy per frame
-        self.graph = None
-        self.out = None
+        self.plans = [model.plan_for(probe, slot=i) for i in range(depth)]
+        self.plan = self.plans[0]
+        self.xs = [p.x_in for p in self.plans]    # the plans' static input slots: no extra device copy per frame
+        self.x = self.xs[0]
+        self.tail_graph = [None] * depth
+        self.out = [None] * depth
+        self.t = 0                                # frames submitted
+        self.tail_stream = torch.cuda.Stream(device=dev) if depth > 1 else None
+        self._ev_dense = [torch.cuda.Event() for _ in range(depth)]
+        self._ev_tail = [torch.cuda.Event() for _ in range(depth)]
         self._copy_stream, self._stage_idx = None, 0
         self.use_cuda_graph = use_cuda_graph
 
     # ------------------------------------------------------------------------------------------
-    def _body(self):
-        """Everything after the image is in self.x; returns the dict of device results."""
-        heads, fms = self.plan.run(self.x)
+    def _tail(self, slot):
+        """Everything after DLASeg.forward for the frame whose activations sit in arena `slot`."""
+        plan = self.plans[slot]
+        heads = plan.head_out
         hm = heads["hm"]
         ops.sigmoid_output_(hm, heads.get("dep"), getattr(self.opt, "depth_scale", 1.0))
         if self.dec_ws is None:
@@ -74,11 +92,11 @@ class FramePipeline:
         oh, ow = hm.shape[2], hm.shape[3]
         centres = ops.boxes_to_centres(d["bboxes"].view(-1, 4), float(ow), float(oh))
         pk = self.model.AFE.packed()
-        emb = ops.afe_extract(self.plan.feature_maps, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres, self.model.AFE.align_corners,
+        emb = ops.afe_extract(plan.feature_maps, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres, self.model.AFE.align_corners,
                               ws=self.ext_ws)
-        ops.afe_affinity(self.memory, self.counts, emb, self.K, self.P, pk["mlp"], out=self.aff, ws=self.aff_ws, flags=self.model.AFE._flags)
+        ops.afe_affinity(self.memory, self.counts, emb, self.K, self.P, pk["mlp"], out=self.aff[slot], ws=self.aff_ws, flags=self.model.AFE._flags)
         res["embeddings"] = emb
-        res["affinity"] = self.aff
+        res["affinity"] = self.aff[slot]
         if self.lstm is not None:
             hn, cn, pred = self.lstm.predict_batch(self.lstm_h, self.lstm_c, self.lstm_x)
             self.lstm_h.copy_(hn)
@@ -86,36 +104,79 @@ class FramePipeline:
             res["lstm_pred"] = pred
         return res
 
+    def _body(self, slot=0):
+        """One whole frame, eagerly, on the current stream (image already in self.xs[slot])."""
+        self.plans[slot].run(self.xs[slot])
+        return self._tail(slot)
+
     def _push_memory(self, emb):
         self.memory[self.head, : self.K].copy_(emb)
         self.head = (self.head + 1) % self.F
 
     def warmup(self):
-        res = self._body()
+        """One eager frame per arena, then (use_cuda_graph) the tails are frozen into CUDA graphs; the dense part is
+        the plan's own graph."""
+        res = None
+        for slot in range(self.depth):
+            if slot > 0:
+                self.xs[slot].copy_(self.xs[0])
+            r = self._body(slot)
+            res = res or r
         torch.cuda.synchronize(self.device)
-        if self.use_cuda_graph and self.graph is None:
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                self._body()
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            with torch.cuda.graph(g):
-                self.out = self._body()
-            self.graph = g
+        if self.use_cuda_graph and self.tail_graph[0] is None:
+            for slot in range(self.depth):
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._tail(slot)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                with torch.cuda.graph(g):
+                    self.out[slot] = self._tail(slot)
+                self.tail_graph[slot] = g
+            torch.cuda.synchronize(self.device)
+        return res
+
+    def _run_tail(self, slot):
+        if self.tail_graph[slot] is not None:
+            self.tail_graph[slot].replay()
+            res = self.out[slot]
+        else:
+            res = self._tail(slot)
+        self._push_memory(res["embeddings"])
         return res
 
     def step_device(self, image_dev=None):
-        """One frame with the image already in HBM (copied into the pipeline's slot if given)."""
-        if image_dev is not None and image_dev.data_ptr() != self.x.data_ptr():
-            self.x.copy_(image_dev, non_blocking=True)
-        if self.graph is not None:
-            self.graph.replay()
-            res = self.out
-        else:
-            res = self._body()
-        self._push_memory(res["embeddings"])
+        """One frame with the image already in HBM (copied into the next arena's input slot if given).  Returns the
+        frame's result tensors (device; complete after a device / tail_stream synchronisation)."""
+        slot = self.t % self.depth
+        self.t += 1
+        main = torch.cuda.current_stream(self.device)
+        if self.depth > 1:
+            main.wait_event(self._ev_tail[slot])          # the frame that last used this arena has finished its tail
+        x = self.xs[slot]
+        if image_dev is not None and image_dev.data_ptr() != x.data_ptr():
+            x.copy_(image_dev, non_blocking=True)
+        self.plans[slot].run(x)
+        if self.depth == 1:
+            return self._run_tail(slot)
+        self._ev_dense[slot].record(main)
+        with torch.cuda.stream(self.tail_stream):
+            self.tail_stream.wait_event(self._ev_dense[slot])
+            res = self._run_tail(slot)
+            self._ev_tail[slot].record(self.tail_stream)
         return res
+
+    def join(self):
+        """Make the caller's stream wait (on the GPU, not the host) for every submitted frame's tail."""
+        if self.tail_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.tail_stream)
+
+    def synchronize(self):
+        """Block the host until every submitted frame is complete."""
+        torch.cuda.current_stream(self.device).synchronize()
+        if self.tail_stream is not None:
+            self.tail_stream.synchronize()
 
     def step(self, image_host, out_host=None):
         """End-to-end frame through the public API: pinned host image in, host results out
@@ -123,7 +184,7 @@ class FramePipeline:
         detector.py:150,545-547 and AFE.py:154-158)."""
         # The upload runs on its own stream into a 2-deep staging ring, so the H2D of frame t+1 overlaps the
         # kernels of frame t whenever the caller does not synchronise between steps (results land in pinned
-        # memory asynchronously; synchronise the stream / device before reading them).
+        # memory asynchronously; synchronise the device / call synchronize() before reading them).
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -139,19 +200,21 @@ class FramePipeline:
             self._stage[j].copy_(image_host, non_blocking=True)
             self._stage_ready[j].record(self._copy_stream)
         cur.wait_event(self._stage_ready[j])
-        self.x.copy_(self._stage[j], non_blocking=True)        # device-to-device, ~3 us
+        res = self.step_device(self._stage[j])                 # device-to-device copy into the arena's slot, ~3 us
         self._stage_free[j].record(cur)
-        res = self.step_device()
         if out_host is None:
             out_host = {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in ("scores", "clses", "bboxes", "affinity")}
-        for k, v in out_host.items():
-            v.copy_(res[k], non_blocking=True)
+        with torch.cuda.stream(self.tail_stream if self.tail_stream is not None else cur):
+            for k, v in out_host.items():
+                v.copy_(res[k], non_blocking=True)
         return out_host
 
     def count_launches(self):
         """Kernel launches of one frame (our kernels only): the library counts every launch it makes
         (deft_launch_count); one eager frame is run between two readings."""
+        torch.cuda.synchronize(self.device)
         before = _lib.lib().deft_launch_count()
-        self._body()
+        self.plans[0].launch()
+        self._tail(0)
         torch.cuda.synchronize(self.device)
         return int(_lib.lib().deft_launch_count() - before)

@@ -176,3 +176,64 @@ def test_c2_full_size_properties(dev):
     ys = [ops.dcnv2_forward(xin, packing.pack_dcn(s, "d.conv"), relu=False).nchw_view() for s in (s1, s2, s3)]
     bias = s1["d.conv.bias"].view(1, -1, 1, 1)
     assert nerr((ys[0] + ys[1] - bias).cpu(), ys[2].cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
+    """FramePipeline (the one-call-per-frame API bench.py times): (1) its detections for a frame are bit-identical
+    to DLASeg.forward -> sigmoid_output -> generic_decode through the reference-named API; (2) its embeddings /
+    affinity equal AFE.forward_feature_extracter / affinity_batched on the same memory; (3) the two-deep
+    software-pipelined mode (dense part of frame t+1 over the tail of frame t, two arenas, two streams) returns
+    exactly what the sequential mode returns, frame by frame, over a sequence long enough to wrap the memory ring."""
+    from deft_b200.model.decode import generic_decode, sigmoid_output
+    from deft_b200.pipeline import FramePipeline
+    heads = spec.MOT_HEADS
+    H, W, K, F = 96, 160, 20, 3
+    frames = [spec.make_input((1, 3, H, W), tag=f"pipe{i}").to(dev) for i in range(7)]
+    results = {}
+    for depth in (1, 2):
+        m, sd, opt = build(heads, "mot", dev, max_object=32, K=K)
+        pipe = FramePipeline(m, opt, H, W, mem_frames=F, device=dev, use_cuda_graph=graph, depth=depth)
+        pipe.xs[0].copy_(frames[0])
+        pipe.warmup()
+        pipe.memory.zero_()
+        pipe.head = 0
+        seq = []
+        for x in frames:
+            r = pipe.step_device(x)
+            pipe.synchronize() if depth == 1 else None      # depth 2: deliberately no sync between frames
+            if depth == 2:
+                # results of frame t must be read before frame t+2 reuses the arena: snapshot on the tail stream
+                with torch.cuda.stream(pipe.tail_stream):
+                    snap = {k: r[k].clone() for k in ("scores", "clses", "bboxes", "embeddings", "affinity")}
+            else:
+                snap = {k: r[k].clone() for k in ("scores", "clses", "bboxes", "embeddings", "affinity")}
+            seq.append(snap)
+        pipe.synchronize()
+        torch.cuda.synchronize(dev)
+        results[depth] = (seq, m, opt)
+    seq1, m, opt = results[1]
+    seq2 = results[2][0]
+    for t, (a, b) in enumerate(zip(seq1, seq2)):
+        for k in a:
+            assert torch.equal(a[k], b[k]), (t, k)
+    # frame 0 against the piecewise public API (fresh memory = zeros)
+    out, fm = m(frames[0])
+    o = sigmoid_output({k: v.clone() for k, v in out[0].items()}, opt)
+    dec = generic_decode(o, K=K, opt=opt)
+    assert torch.equal(dec["scores"], seq1[0]["scores"]) and torch.equal(dec["bboxes"], seq1[0]["bboxes"])
+    assert torch.equal(dec["clses"], seq1[0]["clses"])
+    oh, ow = H // 4, W // 4
+    bb = dec["bboxes"][0]
+    # convert_detection (image.py:391-412) in the kernel's operation order
+    cx = (2.0 * (bb[:, 0] / ow) + (bb[:, 2] - bb[:, 0]) / ow) - 1.0
+    cy = (2.0 * (bb[:, 1] / oh) + (bb[:, 3] - bb[:, 1]) / oh) - 1.0
+    centres = torch.stack([cx, cy], 1).view(1, K, 1, 1, 2)
+    emb = m.AFE.forward_feature_extracter(fm, centres)
+    assert nerr(emb[0].cpu(), seq1[0]["embeddings"].cpu()) < 1e-4
+    # frame 1's affinity: memory holds frame 0's embeddings in ring slot 0, zeros elsewhere
+    mem = torch.zeros((F, 32, emb.shape[2]), device=dev)
+    mem[0, :K] = seq1[0]["embeddings"]
+    aff = m.AFE.affinity_batched(mem, [K] * F, seq1[1]["embeddings"].contiguous())
+    assert aff.shape == seq1[1]["affinity"].shape
+    assert nerr(aff[:, :K, : K + 1].cpu(), seq1[1]["affinity"][:, :K, : K + 1].cpu()) < 1e-4
