@@ -150,7 +150,7 @@ def gpu_arm(args, rank, local_rank, world):
     model = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt).eval()
     randomize_(model, seed=317 + rank)
     model = model.to(dev)
-    pipe = FramePipeline(model, opt, H, W, mem_frames=MEM_FRAMES, device=dev, use_cuda_graph=not args.no_graph, depth=args.depth)
+    pipe = FramePipeline(model, opt, H, W, mem_frames=MEM_FRAMES, device=dev, use_cuda_graph=not args.no_graph, depth=args.depth, dense_streams=args.dense_streams)
     g = torch.Generator(); g.manual_seed(1234 + rank)
     frames_host = [torch.randn((1, 3, H, W), generator=g).pin_memory() for _ in range(4)]    # distinct frames, pinned
     frames_dev = [f.to(dev) for f in frames_host]
@@ -192,6 +192,15 @@ def gpu_arm(args, rank, local_rank, world):
     # (2) end to end through the public API: pinned host frame in, host results out, every copy inside the timed
     #     region; each frame arrives cold from the host and a frame's 1.4 GB working set >> L2, so no extra flush
     ms_e2e, clocks_e2e = timed(lambda i: pipe.step(frames_host[i % 4], out_host))
+    # (2b) latency of ONE isolated frame (submit, then wait for its results): what a depth-1, one-frame-at-a-time caller sees
+    lat = []
+    for i in range(5):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        pipe.step(frames_host[i % 4], out_host)
+        pipe.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    latency_ms = sorted(lat)[len(lat) // 2]
     h2d = frames_host[0].numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
@@ -215,10 +224,11 @@ def gpu_arm(args, rank, local_rank, world):
                 "dtype": "f32" if args.simt else ("tf32" if args.tf32x1 else "f32 (3xTF32 tensor-core where covered, fp32 SIMT elsewhere)"),
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "parallelism": f"stream-parallel x{world} (no collective)",
-                           "cuda_graph": not args.no_graph, "frame_pipelining": f"depth {pipe.depth} (dense part of frame t+1 over the decode/embedding/affinity tail of frame t)",
+                           "cuda_graph": not args.no_graph, "frame_pipelining": f"{pipe.depth} frames of the stream in flight: {pipe.S} dense stream(s) + 1 tail stream (results bit-identical to depth 1, delivered in frame order)",
                            "l2": "no flush: inputs larger than L2 (~1 GB of unique weights + activations per frame vs 126 MB L2, rotating input frames)",
                            "engine": "simt-fp32" if args.simt else "tcgen05"},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "frame_latency_ms": latency_ms,
                 "gpu_launches": launches * args.steps,
                 "gpu_launches_per_step": launches,
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
@@ -247,7 +257,8 @@ def main():
     ap.add_argument("--simt", action="store_true", help="fp32 SIMT anchor engine only")
     ap.add_argument("--tf32x1", action="store_true", help="single-pass TF32 (outside the parity budget)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--depth", type=int, default=2, choices=[1, 2], help="frame software-pipelining depth of the FramePipeline")
+    ap.add_argument("--depth", type=int, default=3, choices=[1, 2, 3, 4], help="FramePipeline: activation arenas = frames of the stream in flight")
+    ap.add_argument("--dense-streams", type=int, default=None, help="FramePipeline: CUDA streams the dense parts rotate over (default 2 when depth >= 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

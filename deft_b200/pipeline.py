@@ -26,14 +26,19 @@ KERNELS_PER_CALL = {  # CUDA kernels launched by each C-ABI entry point (for ben
 
 
 class FramePipeline:
-    """depth=1: everything of a frame on the caller's stream.  depth=2 (default): software pipelining across the
-    frames of ONE video stream -- the dense part (DLASeg: backbone + heads) of frame t+1 runs on the caller's stream
-    while the small-grid tail of frame t (sigmoid, decode, embedding extractor, affinity, LSTM) runs on a second
-    stream over a second activation arena.  Results are identical to depth=1 (same kernels, same order per frame,
-    the embedding memory is only touched by the tail stream, in frame order); a frame's results are complete once the
-    device (or `tail_stream`) has been synchronised."""
+    """Software pipelining across the frames of ONE video stream.  `depth` = activation arenas = frames in flight,
+    `dense_streams` = CUDA streams the dense parts (DLASeg: backbone + heads) rotate over.
+      depth=1                   : everything of a frame on the caller's stream (the reference's order).
+      depth=2, dense_streams=1  : the small-grid tail of frame t (sigmoid, decode, embedding extractor, affinity,
+                                  LSTM) runs on a second stream while frame t+1's dense part runs on the caller's.
+      depth=3, dense_streams=2  : additionally two dense parts overlap (the backbone of frame t+1 does not depend on
+                                  frame t), which fills the SMs the tile tails and small layers of one frame leave idle.
+    The tails always run in frame order on one stream and are the only users of the embedding memory, so every mode
+    returns bit-identical results; a frame's results are complete once the device has been synchronised
+    (`synchronize()`), or after `join()` for work queued behind it on the caller's stream."""
 
-    def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True, depth=2):
+    def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True, depth=3,
+                 dense_streams=None):
         self.model, self.opt = model, opt
         self.device = device or next(model.parameters()).device
         self.H, self.W = height, width
@@ -41,9 +46,12 @@ class FramePipeline:
         self.P = opt.max_object
         if self.K > self.P:
             raise ValueError("K must be <= max_object (forward_stacker_features contract, AFE.py:110-122)")
-        if depth not in (1, 2):
-            raise ValueError("depth must be 1 or 2")
+        if dense_streams is None:
+            dense_streams = 2 if depth >= 3 else 1
+        if not (1 <= depth <= 4 and 1 <= dense_streams <= depth):
+            raise ValueError("need 1 <= dense_streams <= depth <= 4")
         self.depth = depth
+        self.S = dense_streams
         self.F = mem_frames
         self.cemb = sum(model.AFE.selector_output_channel)
         self.lstm, self.T = lstm, lstm_tracks
@@ -69,6 +77,9 @@ class FramePipeline:
         self.out = [None] * depth
         self.t = 0                                # frames submitted
         self.tail_stream = torch.cuda.Stream(device=dev) if depth > 1 else None
+        self.dense_streams = [torch.cuda.Stream(device=dev) for _ in range(self.S)] if self.S > 1 else None
+        self._ev_submit = [torch.cuda.Event() for _ in range(depth)]
+        self._last_dense = None
         self._ev_dense = [torch.cuda.Event() for _ in range(depth)]
         self._ev_tail = [torch.cuda.Event() for _ in range(depth)]
         self._copy_stream, self._stage_idx = None, 0
@@ -148,19 +159,27 @@ class FramePipeline:
 
     def step_device(self, image_dev=None):
         """One frame with the image already in HBM (copied into the next arena's input slot if given).  Returns the
-        frame's result tensors (device; complete after a device / tail_stream synchronisation)."""
+        frame's result tensors (device; complete after synchronize(), or join() + stream order)."""
         slot = self.t % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        ds = cur
+        if self.dense_streams is not None:
+            ds = self.dense_streams[self.t % self.S]
+            self._ev_submit[slot].record(cur)             # the image (and whatever produced it) is ordered before the frame
         self.t += 1
-        main = torch.cuda.current_stream(self.device)
-        if self.depth > 1:
-            main.wait_event(self._ev_tail[slot])          # the frame that last used this arena has finished its tail
+        self._last_dense = ds
         x = self.xs[slot]
-        if image_dev is not None and image_dev.data_ptr() != x.data_ptr():
-            x.copy_(image_dev, non_blocking=True)
-        self.plans[slot].run(x)
-        if self.depth == 1:
-            return self._run_tail(slot)
-        self._ev_dense[slot].record(main)
+        with torch.cuda.stream(ds):
+            if ds is not cur:
+                ds.wait_event(self._ev_submit[slot])
+            if self.depth > 1:
+                ds.wait_event(self._ev_tail[slot])        # the frame that last used this arena has finished its tail
+            if image_dev is not None and image_dev.data_ptr() != x.data_ptr():
+                x.copy_(image_dev, non_blocking=True)
+            self.plans[slot].run(x)
+            if self.depth == 1:
+                return self._run_tail(slot)
+            self._ev_dense[slot].record(ds)
         with torch.cuda.stream(self.tail_stream):
             self.tail_stream.wait_event(self._ev_dense[slot])
             res = self._run_tail(slot)
@@ -169,12 +188,17 @@ class FramePipeline:
 
     def join(self):
         """Make the caller's stream wait (on the GPU, not the host) for every submitted frame's tail."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.dense_streams or []):
+            cur.wait_stream(st)
         if self.tail_stream is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self.tail_stream)
+            cur.wait_stream(self.tail_stream)
 
     def synchronize(self):
         """Block the host until every submitted frame is complete."""
         torch.cuda.current_stream(self.device).synchronize()
+        for st in (self.dense_streams or []):
+            st.synchronize()
         if self.tail_stream is not None:
             self.tail_stream.synchronize()
 
@@ -182,26 +206,27 @@ class FramePipeline:
         """End-to-end frame through the public API: pinned host image in, host results out
         (H2D of the frame, D2H of detections + affinity -- the copies the reference makes at
         detector.py:150,545-547 and AFE.py:154-158)."""
-        # The upload runs on its own stream into a 2-deep staging ring, so the H2D of frame t+1 overlaps the
+        # The upload runs on its own stream into a staging ring (one slot per frame in flight), so the H2D of frame t+1 overlaps the
         # kernels of frame t whenever the caller does not synchronise between steps (results land in pinned
         # memory asynchronously; synchronise the device / call synchronize() before reading them).
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._stage = [torch.empty_like(self.x) for _ in range(2)]
-            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
-            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            ns = max(2, self.depth)                              # staging ring: one slot per frame in flight
+            self._stage = [torch.empty_like(self.x) for _ in range(ns)]
+            self._stage_free = [torch.cuda.Event() for _ in range(ns)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(ns)]
             for e in self._stage_free:
                 e.record(cur)
         j = self._stage_idx
-        self._stage_idx ^= 1
+        self._stage_idx = (j + 1) % len(self._stage)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._stage_free[j])
             self._stage[j].copy_(image_host, non_blocking=True)
             self._stage_ready[j].record(self._copy_stream)
         cur.wait_event(self._stage_ready[j])
         res = self.step_device(self._stage[j])                 # device-to-device copy into the arena's slot, ~3 us
-        self._stage_free[j].record(cur)
+        self._stage_free[j].record(self._last_dense)           # ... on the stream that ran it
         if out_host is None:
             out_host = {k: torch.empty(res[k].shape, dtype=res[k].dtype, pin_memory=True) for k in ("scores", "clses", "bboxes", "affinity")}
         with torch.cuda.stream(self.tail_stream if self.tail_stream is not None else cur):

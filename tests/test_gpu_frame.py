@@ -182,16 +182,15 @@ def test_c2_full_size_properties(dev):
 def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
     """FramePipeline (the one-call-per-frame API bench.py times): (1) its detections for a frame are bit-identical
     to DLASeg.forward -> sigmoid_output -> generic_decode through the reference-named API; (2) its embeddings /
-    affinity equal AFE.forward_feature_extracter / affinity_batched on the same memory; (3) the two-deep
-    software-pipelined mode (dense part of frame t+1 over the tail of frame t, two arenas, two streams) returns
-    exactly what the sequential mode returns, frame by frame, over a sequence long enough to wrap the memory ring."""
+    affinity equal AFE.forward_feature_extracter / affinity_batched on the same memory; (3) the software-pipelined modes (depth 2: dense part of frame t+1 over the tail of frame t; depth 3: two dense
+    parts in flight as well) return exactly what the sequential mode returns, frame by frame, over a sequence long enough to wrap the memory ring."""
     from deft_b200.model.decode import generic_decode, sigmoid_output
     from deft_b200.pipeline import FramePipeline
     heads = spec.MOT_HEADS
     H, W, K, F = 96, 160, 20, 3
     frames = [spec.make_input((1, 3, H, W), tag=f"pipe{i}").to(dev) for i in range(7)]
     results = {}
-    for depth in (1, 2):
+    for depth in (1, 2, 3):
         m, sd, opt = build(heads, "mot", dev, max_object=32, K=K)
         pipe = FramePipeline(m, opt, H, W, mem_frames=F, device=dev, use_cuda_graph=graph, depth=depth)
         pipe.xs[0].copy_(frames[0])
@@ -201,9 +200,8 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
         seq = []
         for x in frames:
             r = pipe.step_device(x)
-            pipe.synchronize() if depth == 1 else None      # depth 2: deliberately no sync between frames
-            if depth == 2:
-                # results of frame t must be read before frame t+2 reuses the arena: snapshot on the tail stream
+            if depth > 1:                                    # deliberately no host sync between frames
+                # results of frame t must be read before frame t+depth reuses the arena: snapshot on the tail stream
                 with torch.cuda.stream(pipe.tail_stream):
                     snap = {k: r[k].clone() for k in ("scores", "clses", "bboxes", "embeddings", "affinity")}
             else:
@@ -213,10 +211,10 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
         torch.cuda.synchronize(dev)
         results[depth] = (seq, m, opt)
     seq1, m, opt = results[1]
-    seq2 = results[2][0]
-    for t, (a, b) in enumerate(zip(seq1, seq2)):
-        for k in a:
-            assert torch.equal(a[k], b[k]), (t, k)
+    for depth in (2, 3):
+        for t, (a, b) in enumerate(zip(seq1, results[depth][0])):
+            for k in a:
+                assert torch.equal(a[k], b[k]), (depth, t, k)
     # frame 0 against the piecewise public API (fresh memory = zeros)
     out, fm = m(frames[0])
     o = sigmoid_output({k: v.clone() for k, v in out[0].items()}, opt)
