@@ -235,3 +235,57 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
     aff = m.AFE.affinity_batched(mem, [K] * F, seq1[1]["embeddings"].contiguous())
     assert aff.shape == seq1[1]["affinity"].shape
     assert nerr(aff[:, :K, : K + 1].cpu(), seq1[1]["affinity"][:, :K, : K + 1].cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("name,heads,dataset,hw,K,F,lstm_tracks", [
+    ("kitti", spec.KITTI_HEADS, "kitti", (384, 1248), 50, 4, 200),        # BASELINE config C3: 1242x375 padded to /32, 50 dets x 200 tracks, LSTM step
+    ("nuscenes", spec.NUSC_HEADS, "nuscenes", (928, 1600), 100, 5, 0),    # BASELINE config C4 per camera: 1600x900 padded to /32
+])
+def test_c3_c4_shapes_pipeline_properties(dev, name, heads, dataset, hw, K, F, lstm_tracks):
+    """BASELINE configs C3 / C4 at full resolution (the CPU oracle is too slow there): the whole FramePipeline runs,
+    every output is finite, decode is sorted with unique peaks, affinity entries are probabilities, and the
+    pipelined mode (3 frames in flight) reproduces the sequential mode bit for bit on a 4-frame sequence."""
+    from deft_b200.kalman_filter_lstm import DecoderRNN, KalmanFilterLSTM
+    from deft_b200.pipeline import FramePipeline
+    H, W = hw
+    frames = [spec.make_input((1, 3, H, W), tag=f"{name}{i}").to(dev) for i in range(4)]
+    seqs = {}
+    for depth in (1, 3):
+        m, sd, opt = build(heads, dataset, dev, max_object=100, K=K)
+        kf = None
+        if lstm_tracks:
+            rnn = DecoderRNN(128, dataset)
+            rnn.load_state_dict(spec.make_state_dict(spec.lstm_spec(dataset), seed=55))
+            kf = KalmanFilterLSTM(opt, rnn.to(dev))
+        pipe = FramePipeline(m, opt, H, W, mem_frames=F, lstm=kf, lstm_tracks=lstm_tracks, device=dev, depth=depth)
+        if lstm_tracks:
+            pipe.lstm_x.copy_(spec.make_input(tuple(pipe.lstm_x.shape), tag="lx").to(dev))
+        pipe.xs[0].copy_(frames[0])
+        pipe.warmup()
+        pipe.memory.zero_()
+        pipe.head = 0
+        if lstm_tracks:
+            pipe.lstm_h.zero_()
+            pipe.lstm_c.zero_()
+        seq = []
+        keys = ["scores", "clses", "bboxes", "embeddings", "affinity"] + (["lstm_pred"] if lstm_tracks else [])
+        for x in frames:
+            r = pipe.step_device(x)
+            with torch.cuda.stream(pipe.tail_stream if pipe.tail_stream is not None else torch.cuda.current_stream(dev)):
+                seq.append({k: r[k].clone() for k in keys})
+        pipe.synchronize()
+        torch.cuda.synchronize(dev)
+        seqs[depth] = seq
+        del pipe, m
+        torch.cuda.empty_cache()
+    for t, (a, b) in enumerate(zip(seqs[1], seqs[3])):
+        for k in a:
+            assert torch.equal(a[k], b[k]), (t, k)
+    last = seqs[1][-1]
+    for k, v in last.items():
+        assert torch.isfinite(v.float()).all(), k
+    s = last["scores"][0]
+    assert s.shape[0] == K and (s[:-1] >= s[1:]).all() and (s > 0).all()
+    aff = last["affinity"][:, :K, : K + 1]
+    assert (aff >= 0).all() and (aff <= 1).all()
+    assert last["embeddings"].shape == (K, 704 if dataset == "nuscenes" else 416)
