@@ -257,8 +257,8 @@ def main():
     ap.add_argument("--simt", action="store_true", help="fp32 SIMT anchor engine only")
     ap.add_argument("--tf32x1", action="store_true", help="single-pass TF32 (outside the parity budget)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, choices=[1, 2, 3, 4], help="FramePipeline: activation arenas = frames of the stream in flight")
-    ap.add_argument("--dense-streams", type=int, default=None, help="FramePipeline: CUDA streams the dense parts rotate over (default 2 when depth >= 3)")
+    ap.add_argument("--depth", type=int, default=4, choices=[1, 2, 3, 4], help="FramePipeline: activation arenas = frames of the stream in flight")
+    ap.add_argument("--dense-streams", type=int, default=None, help="FramePipeline: CUDA streams the dense parts rotate over (default depth - 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

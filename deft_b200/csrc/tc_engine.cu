@@ -839,9 +839,15 @@ int tc_pick_bn(int ldw, int M, int kind) {
     const int max_bn = (kind == TC_KIND_DCN) ? 64 : 128;
     const int mt = ceil_div(M, TC_BM);
     int best = 0;
+    // DEFT_TC_WIDE=1 (default): always the widest dividing tile -- with several frames in flight (FramePipeline) idle SMs
+    // are filled by the other frames' kernels, so fewer, longer CTAs that produce each A tile once win (+2.6 % measured);
+    // 0 = prefer tiles narrow enough to give one launch >= 120 CTAs (better for a single frame in isolation).
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("DEFT_TC_WIDE"); wide = e ? atoi(e) : 1; }
     for (int bn = max_bn; bn >= 32; bn >>= 1) {
         if (ldw % bn != 0) continue;
         if (best == 0) best = bn;                        // largest dividing tile
+        if (wide) return bn;
         if (mt * (ldw / bn) >= 120) return bn;           // enough CTAs for one wave
         if (bn == 64) break;                             // below 64 the redundant A gathers cost more than split-K
     }
@@ -849,8 +855,13 @@ int tc_pick_bn(int ldw, int M, int kind) {
     return best;                                         // too few CTAs either way: keep the widest tile, split K instead
 }
 static int tc_pick_splits(int ctas, int nkb) {
-    if (ctas >= 100) return 1;
-    int s = TC_NUM_SMS / ctas;
+    // CTAs a split-K layer should reach (DEFT_TC_SPLIT_TARGET).  Half the SMs by default: with several frames in flight
+    // the other half is busy with the neighbouring frames' kernels, and every split costs a partial write + read
+    // (measured, 4 frames in flight: 148 -> 487 fps, 74 -> 497 fps, 37 -> 486 fps).
+    static int target = -1;
+    if (target < 0) { const char* e = getenv("DEFT_TC_SPLIT_TARGET"); target = e ? atoi(e) : TC_NUM_SMS / 2; }
+    if (ctas >= 100 || ctas >= target) return 1;
+    int s = target / ctas;
     int max_s = nkb / 6;                                 // keep >= 6 k-blocks per split
     if (s > max_s) s = max_s;
     if (s > 16) s = 16;

@@ -31,7 +31,7 @@ class FramePipeline:
       depth=1                   : everything of a frame on the caller's stream (the reference's order).
       depth=2, dense_streams=1  : the small-grid tail of frame t (sigmoid, decode, embedding extractor, affinity,
                                   LSTM) runs on a second stream while frame t+1's dense part runs on the caller's.
-      depth=3, dense_streams=2  : additionally two dense parts overlap (the backbone of frame t+1 does not depend on
+      depth=3, dense_streams=2  : (default for depth >= 3: dense_streams = depth - 1) additionally two dense parts overlap (the backbone of frame t+1 does not depend on
                                   frame t), which fills the SMs the tile tails and small layers of one frame leave idle.
     The tails always run in frame order on one stream and are the only users of the embedding memory, so every mode
     returns bit-identical results; a frame's results are complete once the device has been synchronised
@@ -47,7 +47,7 @@ class FramePipeline:
         if self.K > self.P:
             raise ValueError("K must be <= max_object (forward_stacker_features contract, AFE.py:110-122)")
         if dense_streams is None:
-            dense_streams = 2 if depth >= 3 else 1
+            dense_streams = max(1, depth - 1)
         if not (1 <= depth <= 4 and 1 <= dense_streams <= depth):
             raise ValueError("need 1 <= dense_streams <= depth <= 4")
         self.depth = depth
