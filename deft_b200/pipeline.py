@@ -18,13 +18,6 @@ import torch
 from . import _lib, ops
 from .model.decode import _REG_HEADS
 
-KERNELS_PER_CALL = {  # CUDA kernels launched by each C-ABI entry point (for bench.py's gpu_launches)
-    "deft_stem_conv7x7": 1, "deft_conv2d_bn_act": 1, "deft_maxpool2x2": 1, "deft_dcnv2_forward": 2, "deft_upsample_add": 1,
-    "deft_heads_forward": 2, "deft_sigmoid_output": 1, "deft_decode": 3, "deft_gather_feat": 1, "deft_boxes_to_centres": 1,
-    "deft_afe_extract": 1, "deft_afe_affinity": 7, "deft_lstm_step": 1,
-}
-
-
 class FramePipeline:
     """Software pipelining across the frames of ONE video stream.  `depth` = activation arenas = frames in flight,
     `dense_streams` = CUDA streams the dense parts (DLASeg: backbone + heads) rotate over.
