@@ -20,6 +20,8 @@ _SIGS = {
     "deft_last_error": (C.c_char_p, []),
     "deft_device_ok": (C.c_int, []),
     "deft_launch_count": (C.c_ulonglong, []),
+    "deft_set_pdl": (None, [C.c_int]),
+    "deft_get_pdl": (C.c_int, []),
     "deft_tc_tile_n": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_blob_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_pack_weights": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp]),

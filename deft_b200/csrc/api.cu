@@ -12,10 +12,26 @@ void set_error(const char* fmt, ...) {
 }
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+// Programmatic dependent launch: -1 = not decided yet (environment DEFT_PDL, default on), 0 / 1 = set.
+static int g_pdl = -1;
+bool pdl_enabled() {
+    int v = __atomic_load_n(&g_pdl, __ATOMIC_RELAXED);
+    if (v < 0) {
+        const char* e = getenv("DEFT_PDL");
+        v = e ? (atoi(e) != 0) : 1;
+        __atomic_store_n(&g_pdl, v, __ATOMIC_RELAXED);
+    }
+    return v != 0;
+}
 }  // namespace deft
 
 extern "C" {
 unsigned long long deft_launch_count(void) { return __atomic_load_n(&deft::g_launches, __ATOMIC_RELAXED); }
+void deft_set_pdl(int enabled) {
+    if (getenv("DEFT_PDL") != nullptr) return;           // an explicit environment setting wins
+    __atomic_store_n(&deft::g_pdl, enabled ? 1 : 0, __ATOMIC_RELAXED);
+}
+int deft_get_pdl(void) { return deft::pdl_enabled() ? 1 : 0; }
 int deft_version(void) { return 100; }
 const char* deft_last_error(void) { return deft::g_err; }
 int deft_device_ok(void) {

@@ -49,11 +49,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define DEFT_PDL_PROLOGUE() do { deft::pdl_wait(); deft::pdl_launch_dependents(); } while (0)
 
-inline bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DEFT_PDL"); v = e ? atoi(e) : 1; }
-    return v != 0;
-}
+bool pdl_enabled();            // api.cu: deft_set_pdl() / DEFT_PDL
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

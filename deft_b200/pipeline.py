@@ -45,6 +45,9 @@ class FramePipeline:
             raise ValueError("need 1 <= dense_streams <= depth <= 4")
         self.depth = depth
         self.S = dense_streams
+        # PDL shortens an isolated frame but early-launched CTAs hold SMs the other frames in flight could use
+        # (measured at depth 4: 497 fps with, 522 fps without); the plans below are captured with this setting
+        _lib.lib().deft_set_pdl(1 if depth == 1 else 0)
         self.F = mem_frames
         self.cemb = sum(model.AFE.selector_output_channel)
         self.lstm, self.T = lstm, lstm_tracks

@@ -50,6 +50,12 @@ const char* deft_last_error(void);
 int deft_device_ok(void);
 /* Total CUDA kernels this library has launched in this process (diagnostics / bench.py's gpu_launches). */
 unsigned long long deft_launch_count(void);
+/* Programmatic dependent launch of the library's kernels (default on; environment DEFT_PDL overrides both).  It
+ * shortens an isolated frame (a kernel's prologue overlaps its predecessor's tail) but costs throughput when several
+ * frames are in flight on different streams (early-launched CTAs hold an SM while they wait), so FramePipeline
+ * switches it off for depth > 1.  Applies to launches (and graph captures) made after the call. */
+void deft_set_pdl(int enabled);
+int deft_get_pdl(void);
 
 /* ---- tcgen05 weight images: a packed weight Wp[K][ldw] re-laid as ready-to-copy shared-memory tiles
  * ([n_tile][k_block][hi|lo][bn x 32] fp32, SWIZZLE_128B, split x = hi + lo for 3xTF32).
