@@ -55,6 +55,35 @@ def test_checkpoint_with_pre_img_layers_and_module_prefix(tmp_path):
     load_model(m2, path, Opt())
 
 
+def test_load_model_resume_semantics_and_shape_mismatch(tmp_path, capsys):
+    """model.py:56-110: a mis-shaped tensor is reported and skipped; with an optimizer the answer is always
+    (model, optimizer, start_epoch), start_epoch 0 unless opt.resume finds an optimizer entry, and the learning rate
+    is re-derived from opt.lr / opt.lr_step."""
+    import types
+    from deft_b200.model.model import create_model, load_model, save_model
+    from deft_b200.opts import Opt
+    heads = spec.MOT_HEADS
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, Opt())
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    bad = "hm.2.weight"
+    sd[bad] = torch.zeros(3, 256, 1, 1)                       # wrong number of classes
+    sd["not.a.key"] = torch.zeros(1)
+    opt_sgd = torch.optim.SGD(m.parameters(), lr=1.0)
+    path = str(tmp_path / "c.pth")
+    torch.save({"epoch": 65, "state_dict": sd, "optimizer": opt_sgd.state_dict()}, path)
+    keep = m.state_dict()[bad].clone()
+    out = load_model(m, path, types.SimpleNamespace(resume=False, lr=1.25e-4, lr_step=[60, 70]), optimizer=opt_sgd)
+    assert isinstance(out, tuple) and out[2] == 0 and opt_sgd.param_groups[0]["lr"] == 1.0
+    assert torch.equal(m.state_dict()[bad], keep)
+    log = capsys.readouterr().out
+    assert "Skip loading parameter " + bad in log and "Drop parameter not.a.key" in log
+    out = load_model(m, path, types.SimpleNamespace(resume=True, lr=1.25e-4, lr_step=[60, 70]), optimizer=opt_sgd)
+    assert out[2] == 65 and abs(opt_sgd.param_groups[0]["lr"] - 1.25e-5) < 1e-12
+    save_model(str(tmp_path / "d.pth"), 66, torch.nn.DataParallel(m), opt_sgd)
+    d = torch.load(str(tmp_path / "d.pth"), weights_only=False)
+    assert d["epoch"] == 66 and "optimizer" in d and not any(k.startswith("module.") for k in d["state_dict"])
+
+
 def test_no_cpu_fallback():
     from deft_b200._lib import DeftError
     from deft_b200.kalman_filter_lstm import DecoderRNN
