@@ -251,8 +251,8 @@ def gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)      # >= 200 timed frames (0.4 s of GPU time)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="deft_b200", choices=["deft_b200", "reference"])
     ap.add_argument("--simt", action="store_true", help="fp32 SIMT anchor engine only")
     ap.add_argument("--tf32x1", action="store_true", help="single-pass TF32 (outside the parity budget)")
