@@ -24,6 +24,25 @@ def test_library_exports_every_declared_symbol():
     assert l.deft_version() >= 100
 
 
+def test_host_only_entry_points_without_a_gpu(monkeypatch):
+    """The C-ABI calls that never touch the device: launch policy switch, tile / blob / scratch sizing."""
+    from deft_b200 import _lib
+    l = _lib.lib()
+    if "DEFT_PDL" not in os.environ:
+        l.deft_set_pdl(0)
+        assert l.deft_get_pdl() == 0
+        l.deft_set_pdl(1)
+        assert l.deft_get_pdl() == 1
+    M = 152 * 272
+    for ldw, kind in ((64, 0), (128, 0), (32, 0), (64, 1)):
+        bn = l.deft_tc_tile_n(ldw, M, kind)
+        assert bn in (16, 32, 64, 128) and ldw % bn == 0
+        assert l.deft_tc_blob_bytes(ldw, 9 * 64, bn) == (ldw // bn) * (9 * 64 // 32) * 2 * bn * 32 * 4     # hi + lo tile images
+    assert l.deft_tc_tile_n(1280, M, 2) == 256                                                         # fused heads: one head per N tile
+    assert l.deft_dcnv2_workspace_bytes(1, 152, 272, 64, 64) >= M * 32 * 4                               # at least the offset/mask map
+    assert l.deft_tc_scratch_bytes(512, 9 * 512, 19 * 34, 0) >= 2 * 19 * 34 * 512 * 4                    # deep layer: split-K partials
+
+
 @pytest.mark.parametrize("heads,dataset", [(spec.MOT_HEADS, "mot"), (spec.KITTI_HEADS, "kitti"), (spec.NUSC_HEADS, "nuscenes")])
 def test_dropin_state_dict_matches_reference(heads, dataset):
     from deft_b200.model.model import create_model
