@@ -3,9 +3,11 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (1 process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+    python bench.py --config c3|c4 [--streams 6]             # the other BASELINE configs / the nuScenes 6-camera split
 
-Workload (BASELINE config C2, "MOT17-shape"): synthetic 1088x608 RGB stream, DLA-34+DCNv2 forward, sigmoid,
-decode K=100, AFE extractor for the 100 detections, affinity against a 5-frame x 100 = 500-embedding track memory.
+Default workload (BASELINE config C2, "MOT17-shape"): synthetic 1088x608 RGB stream (uint8 frames, normalisation
+fused into the stem), DLA-34+DCNv2 forward, sigmoid, decode K=100, AFE extractor for the 100 detections, affinity
+against a 5-frame x 100 = 500-embedding track memory, per-track decayed median -> [500 tracks, 100 dets] cost matrix.
 A step = one frame.  N GPUs = N independent video streams (weak scaling, no collective on the data path).
 Prints ONE JSON line on rank 0.
 """
@@ -19,23 +21,36 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, K_DETS, MEM_FRAMES, MAX_OBJECT = 608, 1088, 100, 5, 100
-P4 = (H // 4) * (W // 4)
-DCN_BYTES_PER_FRAME = 5018.7 * P4 + 13.12e6      # algorithmic HBM bytes of the 16 DCN layers
-METRIC = "frames/sec @1088x608, 100 dets x 500 tracks"
-WORKLOAD = "C2 MOT17-shape 1088x608 stream, DLA-34+DCNv2, K=100 dets, 5x100 track-memory affinity"
+# BASELINE.json configs: input (H, W) as fed to DLASeg, K detections, max_object P, memory = F frames x rows
+CONFIGS = {
+    "c2": dict(name="C2 MOT17-shape 1088x608 stream, DLA-34+DCNv2, K=100 dets, 5x100 = 500-track memory", heads="mot", dataset="mot",
+               H=608, W=1088, K=100, P=100, F=5, rows=100, tracks=500, lstm=0, metric="frames/sec @1088x608, 100 dets x 500 tracks"),
+    "c3": dict(name="C3 KITTI-shape 1242x375 (padded 1248x384) stream, K=50 dets, 4x50 = 200-track memory, LSTM step T=200", heads="kitti",
+               dataset="kitti_tracking", H=384, W=1248, K=50, P=100, F=4, rows=50, tracks=200, lstm=200,
+               metric="frames/sec @1248x384, 50 dets x 200 tracks + LSTM"),
+    "c4": dict(name="C4 nuScenes-shape 1600x900 (padded 1632x928) camera stream, K=300 dets, 4x250 = 1000-track memory, 704-d", heads="nuscenes",
+               dataset="nuscenes", H=928, W=1632, K=300, P=300, F=4, rows=250, tracks=1000, lstm=0,
+               metric="frames/sec @1632x928 per camera stream, 300 dets x 1000 tracks"),
+}
+MEAN, STD = [0.408, 0.447, 0.470], [0.289, 0.274, 0.278]          # the reference's default dataset statistics (generic_dataset.py:67-72)
+
+
+def dcn_bytes(H, W):
+    """algorithmic HBM bytes of the 16 DCN layers of one frame = 5018.7 * P4 + 13.12e6."""
+    return 5018.7 * (H // 4) * (W // 4) + 13.12e6
 
 
 def ncu_traffic():
-    """dram__bytes_read+write per deft_dcnv2_forward launch from the committed ncu --set full capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r1_dcn_ncu_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        return {"traffic": t["dram_bytes_per_launch_avg"], "traffic_source": "profiles/r1_dcn_ncu_traffic.json (ncu --set full, gather-GEMM kernel; "
-                "outputs stay in L2 under ncu's replay, so this is the cold read side)"}
-    except (OSError, KeyError, ValueError):
-        return {"traffic": None}
+    """dram__bytes_read+write per deft_dcnv2_forward gather launch from the newest committed ncu --set full capture (profiles/)."""
+    for fn in ("r2_dcn_ncu_traffic.json", "r1_dcn_ncu_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                t = json.load(f)
+            return {"traffic": t["dram_bytes_per_launch_avg"], "traffic_source": f"profiles/{fn} (ncu --set full, gather-GEMM kernel; outputs stay in "
+                    "L2 under ncu's replay, so this is the cold read side)"}
+        except (OSError, KeyError, ValueError):
+            continue
+    return {"traffic": None}
 
 
 def peaks():
@@ -78,34 +93,80 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+# head tables of the three datasets (opts.py:500-524, kitti_tracking.sh:7), in the reference's order
+HEADS = {"mot": dict(hm=1, reg=2, wh=2, tracking=2, ltrb_amodal=4),
+         "kitti": dict(hm=3, reg=2, wh=2, tracking=2),
+         "nuscenes": dict(hm=10, reg=2, wh=2, tracking=2, dep=1, rot=8, dim=3, amodel_offset=2)}
+
+
+def heads_of(cfg):
+    return dict(HEADS[cfg["heads"]])
+
+
+def afe_dataset(cfg):
+    return "nuscenes" if cfg["dataset"] == "nuscenes" else "mot"      # AFE.py:23: only "nuscenes" changes the embedding widths
+
+
+def synthetic_tracks(T, F, rows, L, clock):
+    """Deterministic node lists for the track reduction: track t was seen in frames (clock-1-q) for q < 1 + t % min(F, L),
+    at detection (7 t + 3 q) % rows -- every track has 1..min(F,L) nodes inside the recorder."""
+    import torch
+    nf = torch.full((T, L), -1, dtype=torch.int32)
+    ni = torch.zeros((T, L), dtype=torch.int32)
+    nc = torch.zeros(T, dtype=torch.int32)
+    for t in range(T):
+        k = 1 + t % min(F, L)
+        for q in range(k):                                 # oldest first
+            nf[t, q] = clock - k + q
+            ni[t, q] = (7 * t + 3 * q) % rows
+        nc[t] = k
+    return nf, ni, nc
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
-def oracle_frame(sd, heads, x, memory, restate, torch):
+def oracle_frame(sd, cfg, x, memory, restate, torch, lstm=None):
     """One frame of the reference algorithm on CPU (oracle/restate.py == the reference's own PyTorch ops)."""
+    heads = heads_of(cfg)
     out, fm = restate.dlaseg_forward(sd, x, heads)
     sig = restate.sigmoid_output(out[0])
-    dec = restate.generic_decode(sig, K=K_DETS)
+    dec = restate.generic_decode(sig, K=cfg["K"])
     oh, ow = sig["hm"].shape[2:]
     centres = restate.convert_detection(dec["bboxes"][0].numpy(), oh, ow)
     emb = restate.afe_extract(sd, fm, centres)
-    affs = [restate.afe_affinity(sd, memory[f:f + 1], emb, MAX_OBJECT, True) for f in range(MEM_FRAMES)]   # tracker.py:76-90
-    return emb, affs
+    affs = [restate.afe_affinity(sd, memory[f:f + 1], emb, cfg["P"], False) for f in range(cfg["F"])]   # tracker.py:76-90
+    if lstm is not None:                                   # tracker.py:467: one track at a time in the reference; batched here (same arithmetic)
+        restate.lstm_predict(*lstm)
+    return out, fm, sig, dec, emb, affs
 
 
-def run_cpu(steps, warmup, budget_s, state_dict=None):
+def cpu_inputs(cfg, torch, spec):
+    cemb = 704 if cfg["dataset"] == "nuscenes" else 416
+    g = torch.Generator(); g.manual_seed(1234)
+    img = torch.randint(0, 256, (1, cfg["H"], cfg["W"], 3), generator=g, dtype=torch.uint8)
+    memory = spec.make_input((cfg["F"], cfg["rows"], cemb), tag="benchmem").abs() * 0.5
+    return img, memory
+
+
+def run_cpu(cfg, steps, warmup, budget_s, state_dict=None, keep_outputs=False):
     import torch
     from oracle import restate, spec
-    heads = spec.MOT_HEADS
+    heads = heads_of(cfg)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = state_dict if state_dict is not None else spec.make_state_dict(spec.dlaseg_spec(heads))
-    x = spec.make_input((1, 3, H, W), tag="bench")
-    memory = spec.make_input((MEM_FRAMES, MAX_OBJECT, 416), tag="benchmem").abs()
-    times = []
+    sd = state_dict if state_dict is not None else spec.make_state_dict(spec.dlaseg_spec(heads, dataset=afe_dataset(cfg)))
+    img, memory = cpu_inputs(cfg, torch, spec)
+    x = restate.normalize_u8(img[0].numpy(), MEAN, STD)
+    lstm = None
+    if cfg["lstm"]:
+        lsd = spec.make_state_dict(spec.lstm_spec(afe_dataset(cfg)), seed=55)
+        T = cfg["lstm"]
+        lstm = (lsd, spec.make_input((T, 128), tag="bh") * 0.1, spec.make_input((T, 128), tag="bc") * 0.1, spec.make_input((T, 11), tag="bx"), 5)
+    times, outputs = [], None
     t_start = time.time()
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.time()
-            emb, _ = oracle_frame(sd, heads, x, memory, restate, torch)
+            outputs = oracle_frame(sd, cfg, x, memory, restate, torch, lstm)
             dt = time.time() - t0
             if i >= warmup:
                 times.append(dt)
@@ -113,52 +174,95 @@ def run_cpu(steps, warmup, budget_s, state_dict=None):
                 break
     n = len(times)
     total = sum(times)
-    return {"fps": n / total, "steps": n, "ms_per_step": 1000 * total / n, "cores": torch.get_num_threads()}
+    r = {"fps": n / total, "steps": n, "ms_per_step": 1000 * total / n, "cores": torch.get_num_threads()}
+    if keep_outputs:
+        r["outputs"] = outputs
+        r["memory"] = memory
+        r["img"] = img
+    return r
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
-    r = run_cpu(args.steps, min(args.warmup, 1), budget_s=150.0)
-    line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"],
-            "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+    cfg = CONFIGS[args.config]
+    r = run_cpu(cfg, args.steps, min(args.warmup, 1), budget_s=200.0)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"],
+            "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (oracle port of the reference's PyTorch modules; "
-                                                     "DCN = torchvision.ops.deform_conv2d since upstream DCNv2 is un-vendored); "
-                                                     "timed steps bounded to ~150 s"},
-            "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": f"{r['steps']} full C2 frames"},
+            "config": {"workload": cfg["name"], "note": "reference algorithm on host CPU cores (oracle port of the reference's PyTorch modules; "
+                                                        "DCN = torchvision.ops.deform_conv2d since upstream DCNv2 is un-vendored); one step = one "
+                                                        "full frame, the run is bounded to ~200 s so fewer than --steps frames may be timed"},
+            "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": f"{r['steps']} full {args.config.upper()} frames"},
             "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def build_pipeline(args, cfg, dev, seed, torch):
+    from deft_b200.kalman_filter_lstm import DecoderRNN, KalmanFilterLSTM
+    from deft_b200.model.model import create_model
+    from deft_b200.opts import Opt
+    from deft_b200.pipeline import FramePipeline
+    from deft_b200.synthetic import randomize_
+    heads = heads_of(cfg)
+    opt = Opt(dataset=cfg["dataset"], K=cfg["K"], max_object=cfg["P"], heads=heads, tensor_core=not args.simt, tf32x1=args.tf32x1)
+    model = create_model("dla_34", heads, {h: [256] for h in heads}, opt).eval()
+    randomize_(model, seed=seed)
+    model = model.to(dev)
+    kf = None
+    if cfg["lstm"]:
+        rnn = DecoderRNN(128, "mot")
+        g = torch.Generator(); g.manual_seed(55)
+        with torch.no_grad():
+            for p in rnn.parameters():
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) / 128 ** 0.5)
+        kf = KalmanFilterLSTM(opt, rnn.to(dev))
+    pipe = FramePipeline(model, opt, cfg["H"], cfg["W"], mem_frames=cfg["F"], mem_rows=cfg["rows"], lstm=kf, lstm_tracks=cfg["lstm"], device=dev,
+                         use_cuda_graph=not args.no_graph, depth=args.depth, dense_streams=args.dense_streams,
+                         tracks=0 if args.no_tracks else cfg["tracks"], uint8_norm=None if args.fp32_input else (MEAN, STD))
+    return model, pipe, opt
+
+
 def gpu_arm(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from deft_b200.model.model import create_model
-    from deft_b200.opts import Opt
-    from deft_b200.parallel import aggregate_throughput
-    from deft_b200.pipeline import FramePipeline
-    from deft_b200.synthetic import randomize_
+    from deft_b200 import _lib
+    from deft_b200.parallel import aggregate_throughput, stream_assignment
 
+    cfg = CONFIGS[args.config]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    opt = Opt(K=K_DETS, max_object=MAX_OBJECT, tensor_core=not args.simt, tf32x1=args.tf32x1)
-    heads = opt.heads
-    model = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt).eval()
-    randomize_(model, seed=317 + rank)
-    model = model.to(dev)
-    pipe = FramePipeline(model, opt, H, W, mem_frames=MEM_FRAMES, device=dev, use_cuda_graph=not args.no_graph, depth=args.depth, dense_streams=args.dense_streams)
-    g = torch.Generator(); g.manual_seed(1234 + rank)
-    frames_host = [torch.randn((1, 3, H, W), generator=g).pin_memory() for _ in range(4)]    # distinct frames, pinned
-    frames_dev = [f.to(dev) for f in frames_host]
-    pipe.x.copy_(frames_dev[0])
-    pipe.warmup()
-    out_host = None
-    for i in range(max(args.warmup, 3)):
-        out_host = pipe.step(frames_host[i % 4], out_host)
+    # streams owned by this rank: --streams N_total deals N video streams round-robin over the ranks (C4: 6 cameras over 2/4/8 GPUs);
+    # default = one stream per GPU (weak scaling)
+    my_streams = stream_assignment(args.streams, world, rank) if args.streams else [rank]
+    n_total_streams = args.streams if args.streams else world
+    S = len(my_streams)
+    pipes, models, frames_host, frames_dev, out_hosts, cstreams = [], [], [], [], [], []
+    for sid in my_streams:
+        model, pipe, opt = build_pipeline(args, cfg, dev, 317 + sid, torch)
+        g = torch.Generator(); g.manual_seed(1234 + sid)
+        if args.fp32_input:
+            fh = [torch.randn((1, 3, cfg["H"], cfg["W"]), generator=g).pin_memory() for _ in range(4)]
+        else:
+            fh = [torch.randint(0, 256, (1, cfg["H"], cfg["W"], 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        fd = [f.to(dev) for f in fh]
+        st = torch.cuda.Stream(device=dev) if S > 1 else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st):
+            pipe.x.copy_(fd[0])
+            pipe.warmup()
+            cemb = pipe.cemb
+            mem = (torch.randn((cfg["F"], cfg["rows"], cemb), generator=torch.Generator().manual_seed(99 + sid)).abs() * 0.5).to(dev)
+            pipe.prefill_memory(mem)
+            if pipe.T_tracks:
+                nf, ni, nc = synthetic_tracks(pipe.T_tracks, cfg["F"], cfg["rows"], _lib.lib().deft_track_nodes_per_track(), cfg["F"])
+                pipe.set_tracks(nf, ni, nc)
+            oh = None
+            for i in range(max(args.warmup, 3)):
+                oh = pipe.step(fh[i % 4], oh)
+        pipes.append(pipe); models.append(model); frames_host.append(fh); frames_dev.append(fd); out_hosts.append(oh); cstreams.append(st)
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -167,85 +271,164 @@ def gpu_arm(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     def timed(step_fn):
-        """K back-to-back steps between one CUDA-event pair on the launching stream (the pipeline's second stream is
-        joined into it before the closing event), barrier + device synchronize on both sides, max over ranks.
-        No L2 flush: one frame touches ~1 GB of unique bytes (0.33 GB packed weights + tile images, 0.8 GB
-        activation arena, two arenas alternating) >> 126 MB L2, and the input frames rotate."""
+        """K back-to-back steps per stream between one CUDA-event pair on the launching stream (all pipeline streams are
+        joined into it before the closing event), barrier + device synchronize on both sides, max over ranks.  A second
+        event after every frame's tail gives the per-frame completion intervals (median / p95).
+        No L2 flush: one frame touches ~1 GB of unique bytes (0.33 GB packed weights + tile images, 0.8 GB activation
+        arena, `depth` arenas rotating) >> 126 MB L2, and the input frames rotate."""
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
+        main = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        marks = [[] for _ in pipes]
+        e0.record(main)
+        for st in cstreams:
+            if st is not main:
+                st.wait_event(e0)
         for i in range(args.steps):
-            step_fn(i)
-        pipe.join()
-        e1.record()
+            for s, pipe in enumerate(pipes):
+                with torch.cuda.stream(cstreams[s]):
+                    step_fn(s, i)
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(pipe.tail_stream if pipe.tail_stream is not None else cstreams[s])
+                    marks[s].append(ev)
+        for s, pipe in enumerate(pipes):
+            with torch.cuda.stream(cstreams[s]):
+                pipe.join()
+            if cstreams[s] is not main:
+                main.wait_stream(cstreams[s])
+        e1.record(main)
         barrier()
         sampler.stop_flag = True
         sampler.join()
         ms = e0.elapsed_time(e1)
-        _, ms_max = aggregate_throughput(float(args.steps), ms, device=dev)      # max over ranks of the device time
-        return ms_max, sampler.summary()
+        iv = []
+        for m in marks:
+            iv += [m[i].elapsed_time(m[i + 1]) for i in range(len(m) - 1)]
+        iv.sort()
+        stats = {"frame_interval_ms_median": iv[len(iv) // 2] if iv else None, "frame_interval_ms_p95": iv[min(len(iv) - 1, int(0.95 * len(iv)))] if iv else None}
+        _, ms_max = aggregate_throughput(float(args.steps * S), ms, device=dev)      # max over ranks of the device time
+        return ms_max, sampler.summary(), stats
 
     # (1) device-resident value: frames already in HBM
-    ms_dev, clocks = timed(lambda i: pipe.step_device(frames_dev[i % 4]))
+    ms_dev, clocks, stats_dev = timed(lambda s, i: pipes[s].step_device(frames_dev[s][i % 4]))
     # (2) end to end through the public API: pinned host frame in, host results out, every copy inside the timed
-    #     region; each frame arrives cold from the host and a frame's 1.4 GB working set >> L2, so no extra flush
-    ms_e2e, clocks_e2e = timed(lambda i: pipe.step(frames_host[i % 4], out_host))
-    # (2b) latency of ONE isolated frame (submit, then wait for its results): what a depth-1, one-frame-at-a-time caller sees
-    lat = []
-    for i in range(5):
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        pipe.step(frames_host[i % 4], out_host)
-        pipe.synchronize()
-        lat.append((time.perf_counter() - t0) * 1e3)
-    latency_ms = sorted(lat)[len(lat) // 2]
-    h2d = frames_host[0].numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
-
-    # (3) per-kernel DCN timing for the roofline: CUDA events around every deft_dcnv2_forward of the eager launch list
-    dcn_ms = []
-    for _ in range(3):
-        prof = pipe.plan.launch_profiled()
-        dcn_ms.append(sum(ms for name, _, ms in prof if name == "deft_dcnv2_forward"))
-    dcn_ms = sorted(dcn_ms)[1]
-    peak, peak_src = peaks()
-    achieved = DCN_BYTES_PER_FRAME / (dcn_ms * 1e-3) / 1e9
-    n_dcn = sum(1 for name, _, _ in prof if name == "deft_dcnv2_forward")
-    launches = pipe.count_launches()
-
+    #     region; each frame arrives cold from the host and a frame's working set >> L2, so no extra flush
+    ms_e2e, clocks_e2e, stats_e2e = timed(lambda s, i: pipes[s].step(frames_host[s][i % 4], out_hosts[s]))
     line = None
+    if S >= 1:
+        pipe = pipes[0]
+        # (2b) latency of ONE isolated frame (submit, then wait for its results): what a one-frame-at-a-time caller sees
+        lat = []
+        for i in range(5):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            pipe.step(frames_host[0][i % 4], out_hosts[0])
+            pipe.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        latency_ms = sorted(lat)[len(lat) // 2]
+        h2d = frames_host[0][0].numel() * frames_host[0][0].element_size()
+        d2h = sum(v.numel() * v.element_size() for v in out_hosts[0].values())
+        # (3) per-kernel DCN timing for the roofline: CUDA events around every deft_dcnv2_forward of the eager launch list
+        dcn_ms = []
+        for _ in range(3):
+            prof = pipe.plan.launch_profiled()
+            dcn_ms.append(sum(ms for name, _, ms in prof if name == "deft_dcnv2_forward"))
+        dcn_ms = sorted(dcn_ms)[1]
+        n_dcn = sum(1 for name, _, _ in prof if name == "deft_dcnv2_forward")
+        launches = pipe.count_launches()
+    peak, peak_src = peaks()
+    total_frames = None
+    if world > 1:
+        t = torch.tensor([float(args.steps * S)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        total_frames = float(t.item())
+    else:
+        total_frames = float(args.steps * S)
+
     if rank == 0:
-        fps = world * args.steps / (ms_dev * 1e-3)
-        fps_e2e = world * args.steps / (ms_e2e * 1e-3)
-        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        B = dcn_bytes(cfg["H"], cfg["W"])
+        achieved = B / (dcn_ms * 1e-3) / 1e9
+        fps = total_frames / (ms_dev * 1e-3)
+        fps_e2e = total_frames / (ms_e2e * 1e-3)
+        line = {"metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if args.simt else ("tf32" if args.tf32x1 else "f32 (3xTF32 tensor-core where covered, fp32 SIMT elsewhere)"),
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "parallelism": f"stream-parallel x{world} (no collective)",
-                           "cuda_graph": not args.no_graph, "frame_pipelining": f"{pipe.depth} frames of the stream in flight: {pipe.S} dense stream(s) + 1 tail stream (results bit-identical to depth 1, delivered in frame order)",
+                "config": {"workload": cfg["name"], "streams_total": n_total_streams, "streams_per_gpu": S if world == 1 or not args.streams else f"{n_total_streams} streams round-robin over {world} GPUs",
+                           "parallelism": f"stream-parallel, {n_total_streams} stream(s) over {world} GPU(s) (no collective)",
+                           "cuda_graph": not args.no_graph, "input": "fp32 NCHW (pre-normalised)" if args.fp32_input else "uint8 HWC, normalisation fused into the stem",
+                           "track_reduction": (not args.no_tracks) and cfg["tracks"],
+                           "frame_pipelining": f"{pipes[0].depth} frames of a stream in flight: {pipes[0].S} dense stream(s) + 1 tail stream (results bit-identical to depth 1, delivered in frame order)",
                            "l2": "no flush: inputs larger than L2 (~1 GB of unique weights + activations per frame vs 126 MB L2, rotating input frames)",
                            "engine": "simt-fp32" if args.simt else "tcgen05"},
-                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, **stats_e2e},
+                **stats_dev,
                 "frame_latency_ms": latency_ms,
-                "gpu_launches": launches * args.steps,
+                "gpu_launches": launches * args.steps * S,
                 "gpu_launches_per_step": launches,
+                "simt_fallbacks": int(_lib.lib().deft_simt_fallback_count()),
                 "clocks": clocks, "clocks_e2e": clocks_e2e,
                 "roofline": {"bound": "hbm", "kernel": "deft_dcnv2_forward (offset/mask conv + fused gather-GEMM), 16 layers/frame",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                             "algorithmic_bytes_per_frame": DCN_BYTES_PER_FRAME, "dcn_ms_per_frame": dcn_ms, "dcn_layers": n_dcn,
-                             "algorithmic_bytes_per_launch": DCN_BYTES_PER_FRAME / max(n_dcn, 1), "launch_ms_avg": dcn_ms / max(n_dcn, 1),
+                             "algorithmic_bytes_per_frame": B, "dcn_ms_per_frame": dcn_ms, "dcn_layers": n_dcn,
+                             "algorithmic_bytes_per_launch": B / max(n_dcn, 1), "launch_ms_avg": dcn_ms / max(n_dcn, 1),
                              **ncu_traffic()}}
         if world == 1 and not args.no_cpu_baseline:
-            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-            r = run_cpu(2, 0, budget_s=40.0, state_dict=sd)
-            line["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                                    "sample": f"{r['steps']} full C2 frames of the oracle (reference modules' PyTorch-CPU arithmetic, DCN=torchvision deform_conv2d)"}
+            line.update(cpu_leg_with_parity(args, cfg, models[0], pipes[0], dev, torch))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_leg_with_parity(args, cfg, model, pipe, dev, torch):
+    """The cpu_baseline leg (oracle = the reference's arithmetic on the host cores, bounded sample) -- and, since it computes a
+    full frame on the SAME weights, a parity check of the GPU frame against it: the same uint8 frame goes through the
+    pipeline (depth as benchmarked) and every head, FeatureMap, the embeddings and the affinity blocks are compared."""
+    from oracle import restate
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    r = run_cpu(cfg, 2, 0, budget_s=60.0, state_dict=sd, keep_outputs=True)
+    out = {"cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                            "sample": f"{r['steps']} full {args.config.upper()} frames of the oracle (reference modules' PyTorch-CPU arithmetic, DCN=torchvision deform_conv2d)"}}
+    ref_out, ref_fm, sig, dref, e_ref, a_ref = r["outputs"]
+    img, memory = r["img"], r["memory"]
+    pipe.prefill_memory(memory.to(dev))
+    if args.fp32_input:
+        frame = restate.normalize_u8(img[0].numpy(), MEAN, STD).to(dev)
+    else:
+        frame = img.to(dev)
+    slot = pipe.t % pipe.depth
+    res = pipe.step_device(frame)
+    pipe.synchronize()
+    torch.cuda.synchronize(dev)
+
+    def nerr(a, b):
+        a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double()
+        s = float(b.abs().max())
+        return float((a - b).abs().max()) / (s if s > 0 else 1.0)
+    errs = {}
+    plan = pipe.plans[slot]
+    for h in ref_out[0]:
+        errs[h] = nerr(plan.head_out[h], sig[h] if h in ("hm", "dep") else ref_out[0][h])
+    for i in range(13):
+        errs[f"fm{i}"] = nerr(plan.fm_views[i], ref_fm[i])
+    oh, ow = cfg["H"] // 4, cfg["W"] // 4
+    with torch.no_grad():
+        centres = restate.convert_detection(res["bboxes"][0].cpu().numpy(), oh, ow)
+        errs["emb"] = nerr(res["embeddings"], restate.afe_extract(sd, ref_fm, centres)[0])
+        emb_gpu = res["embeddings"].cpu()[None]
+        errs["aff"] = max(nerr(res["affinity"][f, : cfg["rows"], : cfg["K"] + 1],
+                               restate.afe_affinity(sd, memory[f:f + 1], emb_gpu, cfg["P"], False)) for f in range(cfg["F"]))
+    from deft_b200.model.decode import generic_decode
+    dsh = generic_decode({k: v.to(dev) for k, v in sig.items()}, K=cfg["K"], opt=pipe.opt)
+    decode_exact = all(torch.equal(dsh[k].cpu(), dref[k]) for k in ("scores", "clses", "xs", "ys", "bboxes"))
+    same = int(((res["xs"][0].cpu() == dref["xs"][0]) & (res["ys"][0].cpu() == dref["ys"][0])).sum())
+    out["parity"] = {"max_nerr": max(errs.values()), "worst": max(errs, key=errs.get), "decode_exact": bool(decode_exact),
+                     "same_detections": f"{same}/{cfg['K']}", "tolerance": 1e-3, "through": f"FramePipeline(depth={pipe.depth}), same weights and frame as the cpu_baseline leg",
+                     "tensors": len(errs)}
+    return out
 
 
 def main():
@@ -254,9 +437,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)      # >= 200 timed frames (0.4 s of GPU time)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="deft_b200", choices=["deft_b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS), help="BASELINE.json config (default c2 = the config the metric is quoted on)")
+    ap.add_argument("--streams", type=int, default=0, help="total independent video streams dealt round-robin over the GPUs (C4: 6 cameras); 0 = one per GPU")
     ap.add_argument("--simt", action="store_true", help="fp32 SIMT anchor engine only")
     ap.add_argument("--tf32x1", action="store_true", help="single-pass TF32 (outside the parity budget)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--fp32-input", action="store_true", help="pre-normalised fp32 NCHW frames (round-1 input path) instead of uint8 HWC")
+    ap.add_argument("--no-tracks", action="store_true", help="skip the per-track similarity reduction (D2H = raw affinity blocks, as in round 1)")
     ap.add_argument("--depth", type=int, default=4, choices=[1, 2, 3, 4], help="FramePipeline: activation arenas = frames of the stream in flight")
     ap.add_argument("--dense-streams", type=int, default=None, help="FramePipeline: CUDA streams the dense parts rotate over (default depth - 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

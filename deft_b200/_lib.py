@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeft_b200.so")
+# DEFT_B200_LIB: an alternative build of the same library (A/B experiments: tools/), never a different implementation
+LIB_PATH = os.environ.get("DEFT_B200_LIB") or os.path.join(_HERE, "libdeft_b200.so")
 
 c_fp = C.c_void_p   # device pointers travel as integers
 c_int_p = C.POINTER(C.c_int)
@@ -21,6 +22,9 @@ _SIGS = {
     "deft_device_ok": (C.c_int, []),
     "deft_launch_count": (C.c_ulonglong, []),
     "deft_set_pdl": (None, [C.c_int]),
+    "deft_simt_fallback_count": (C.c_ulonglong, []),
+    "deft_debug_set_engine_log": (None, [C.c_int]),
+    "deft_debug_set_trace": (None, [c_fp]),
     "deft_get_pdl": (C.c_int, []),
     "deft_tc_tile_n": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "deft_tc_blob_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -52,6 +56,24 @@ _SIGS = {
     "deft_afe_affinity_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "deft_afe_affinity": (C.c_int, [c_fp, c_int_p, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
                                     c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float, c_ptr_p, c_int_p, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),
+    "deft_afe_pairs_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "deft_afe_project": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_ptr_p, c_int_p, c_fp, c_fp, C.c_uint, c_fp]),
+    "deft_afe_affinity_cached": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                           c_fp, c_fp, c_fp, C.c_float, c_ptr_p, c_int_p, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),
+    "deft_afe_forward_scores": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_float,
+                                          c_ptr_p, c_int_p, C.c_float, c_fp, C.c_uint, c_fp, C.c_size_t, c_fp]),
+    "deft_afe_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "deft_afe_loss": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
+    "deft_track_nodes_per_track": (C.c_int, []),
+    "deft_memory_push": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "deft_track_similarity": (C.c_int, [c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, C.c_int,
+                                        C.c_int, C.c_double, C.c_double, c_fp, c_fp, c_fp]),
+    "deft_track_append": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp, c_fp]),
+    "deft_count_above": (C.c_int, [c_fp, C.c_int, C.c_float, c_fp, c_fp]),
+    "deft_stem_conv7x7_u8": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_fp, c_fp, c_fp, c_fp, C.c_int,
+                                       c_fp, c_fp]),
+    "deft_preprocess_warp": (C.c_int, [c_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), c_fp, C.c_int,
+                                       C.c_int, c_fp]),
     "deft_lstm_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int,
                                  c_fp, c_fp, c_fp, c_fp]),
 }
@@ -101,6 +123,10 @@ def require_device(t):
         raise DeftError(lib().deft_last_error().decode())
 
 
+def float_array(vals):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
 def int_array(vals):
     return (C.c_int * len(vals))(*vals)
 
@@ -109,6 +135,36 @@ def ptr_array(vals):
     return (C.c_void_p * len(vals))(*vals)
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream of `device` (a torch.device / index / tensor; default: the current device).  Kernels
+    must run on a stream of the device that owns their pointers -- callers pass the tensor they launch on."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    if device is not None and hasattr(device, "device"):
+        device = device.device
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """`with on_device(t):` -- make t's device current for the enclosed C-ABI calls (cudaFuncSetAttribute, launches and
+    cuTensorMapEncode act on the CURRENT device) and give the stream of that device.  A no-op when it already is."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, t):
+        import torch
+        d = t.device if hasattr(t, "device") else t
+        self.dev = d.index if d.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        import torch
+        cur = torch.cuda.current_device()
+        if cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            import torch
+            torch.cuda.set_device(self.prev)
+        return False

@@ -23,9 +23,32 @@ bool pdl_enabled() {
     }
     return v != 0;
 }
+static long long* g_trace = nullptr;
+long long* debug_trace_ptr() { return __atomic_load_n(&g_trace, __ATOMIC_RELAXED); }
+static unsigned long long g_fallbacks = 0;
+static int g_engine_log = -1;
+void note_simt_fallback(const char* op, const char* fmt, ...) {
+    __atomic_fetch_add(&g_fallbacks, 1ull, __ATOMIC_RELAXED);
+    int v = __atomic_load_n(&g_engine_log, __ATOMIC_RELAXED);
+    if (v < 0) {
+        const char* e = getenv("DEFT_DEBUG_ENGINE");
+        v = e ? (atoi(e) != 0) : 0;
+        __atomic_store_n(&g_engine_log, v, __ATOMIC_RELAXED);
+    }
+    if (!v) return;
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "deft_b200: %s served by the fp32 SIMT engine (tcgen05 dispatcher declined: %s)\n", op, buf);
+}
 }  // namespace deft
 
 extern "C" {
+void deft_debug_set_trace(void* device_buffer) { __atomic_store_n(&deft::g_trace, reinterpret_cast<long long*>(device_buffer), __ATOMIC_RELAXED); }
+void deft_debug_set_engine_log(int enabled) { __atomic_store_n(&deft::g_engine_log, enabled ? 1 : 0, __ATOMIC_RELAXED); }
+unsigned long long deft_simt_fallback_count(void) { return __atomic_load_n(&deft::g_fallbacks, __ATOMIC_RELAXED); }
 unsigned long long deft_launch_count(void) { return __atomic_load_n(&deft::g_launches, __ATOMIC_RELAXED); }
 void deft_set_pdl(int enabled) {
     if (getenv("DEFT_PDL") != nullptr) return;           // an explicit environment setting wins

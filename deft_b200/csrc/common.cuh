@@ -33,6 +33,28 @@ inline cudaStream_t to_stream(deft_stream_t s) { return reinterpret_cast<cudaStr
         }                                                                         \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel, so what has been granted is
+// remembered per device ordinal (a process may drive several GPUs through this library).  `granted` is the caller's
+// function-local static (one per kernel instantiation).  Requests <= 48 KB need no attribute.
+constexpr int DEFT_MAX_DEVICES = 64;
+template <typename K>
+inline int ensure_dyn_smem(K kernel, size_t bytes, size_t (&granted)[DEFT_MAX_DEVICES], const char* what) {
+    if (bytes <= 48 * 1024) return DEFT_OK;
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= DEFT_MAX_DEVICES) {
+        set_error("%s: cannot identify the current device", what);
+        return DEFT_ECUDA;
+    }
+    if (bytes <= granted[d]) return DEFT_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cannot raise the dynamic shared memory limit to %zu bytes: %s", what, bytes, cudaGetErrorString(e));
+        return DEFT_ECUDA;
+    }
+    granted[d] = bytes;
+    return DEFT_OK;
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -50,6 +72,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 #define DEFT_PDL_PROLOGUE() do { deft::pdl_wait(); deft::pdl_launch_dependents(); } while (0)
 
 bool pdl_enabled();            // api.cu: deft_set_pdl() / DEFT_PDL
+long long* debug_trace_ptr();  // api.cu: deft_debug_set_trace(); nullptr unless a bring-up tool armed it
+// A tensor-core dispatcher that answers DEFT_EINVAL ("shape not covered") makes the caller fall back to the fp32 SIMT
+// engine: correct, but ~7x slower.  Every such fallback is counted (deft_simt_fallback_count) and, with
+// DEFT_DEBUG_ENGINE=1 / deft_debug_set_engine_log(1), reported on stderr, so a shape regression cannot hide.
+void note_simt_fallback(const char* op, const char* detail_fmt, ...);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

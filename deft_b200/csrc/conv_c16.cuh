@@ -100,10 +100,10 @@ template <int COUT, int STRIDE, int PX>
 inline int launch_conv3x3_c16(const float* x, int x_pitch, int N, int H, int W, int OH, int OW, const float* wp, int ldw, const float* scale,
                               const float* shift, float* out, int out_pitch, int relu, cudaStream_t st) {
     using Cfg = C16Cfg<COUT, STRIDE, PX>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(conv3x3_c16_kernel<COUT, STRIDE, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        attr_done = true;
+    static size_t granted[DEFT_MAX_DEVICES] = {};
+    {
+        const int rc_attr = ensure_dyn_smem(conv3x3_c16_kernel<COUT, STRIDE, PX>, Cfg::SMEM_BYTES, granted, "conv3x3_c16");
+        if (rc_attr != DEFT_OK) return rc_attr;
     }
     dim3 grid(ceil_div(OW, Cfg::TW), ceil_div(OH, Cfg::TH), N);
     launch_pdl(conv3x3_c16_kernel<COUT, STRIDE, PX>, dim3(grid), dim3(128), Cfg::SMEM_BYTES, st, x, x_pitch, H, W, OH, OW, wp, ldw, scale, shift, out, out_pitch, relu);

@@ -135,8 +135,9 @@ struct DcnAP {
 constexpr int AFF_MAX_FRAMES = 64;
 struct PairAP {
     const float* au;  // [F*P, 512]
-    const float* bv;  // [P, 512]
+    const float* bv;  // [P, 512] (+ f * bvf: one current frame per memory frame in the batched training forward, a9)
     int P, m, F, ld;
+    long long bvf;    // element stride of bv between frames; 0 = every frame meets the same current detections
     int off[AFF_MAX_FRAMES + 1];  // prefix offsets of n_f*m
     static constexpr int kExtraSmemBytes = 0;
     const float* pa_[2];
@@ -154,7 +155,7 @@ struct PairAP {
                 int q = p - off[f];
                 int ii = q / m, jj = q - ii * m;
                 pa_[i] = au + ((size_t)f * P + ii) * ld;
-                pb_[i] = bv + (size_t)jj * ld;
+                pb_[i] = bv + (size_t)f * bvf + (size_t)jj * ld;
             }
         }
     }
@@ -268,10 +269,10 @@ __global__ void __launch_bounds__(IG_THREADS) igemm_simt_kernel(AP ap, const flo
 template <class AP, int BN>
 inline int launch_igemm_bn(const AP& ap, const float* Wp, int ldw, int K, int M, const Epilogue& ep, cudaStream_t st) {
     size_t smem = (size_t)(2 * IG_BM * IG_ALD + 2 * IG_BK * BN) * sizeof(float) + AP::kExtraSmemBytes;
-    static bool attr_done = false;  // per template instantiation
-    if (!attr_done) {
-        cudaFuncSetAttribute(igemm_simt_kernel<AP, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+    static size_t granted[DEFT_MAX_DEVICES] = {};  // per template instantiation and device
+    {
+        const int rc_attr = ensure_dyn_smem(igemm_simt_kernel<AP, BN>, smem, granted, "igemm_simt_kernel");
+        if (rc_attr != DEFT_OK) return rc_attr;
     }
     dim3 grid(ceil_div(M, IG_BM), ldw / BN);
     igemm_simt_kernel<AP, BN><<<grid, IG_THREADS, smem, st>>>(ap, Wp, ldw, K, M, ep);

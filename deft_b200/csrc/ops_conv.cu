@@ -297,6 +297,7 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
     if (flags & DEFT_FLAG_TENSORCORE) {
         int rc = tc_conv_dispatch(ap, w_tc, tc_bn, ldw, K, M, ep, flags, ws, ws_bytes, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;   // EINVAL from the TC engine = shape not covered -> SIMT
+        note_simt_fallback("deft_conv2d_bn_act", "Ctot=%d Cout=%d k=%dx%d s=%d M=%d bn=%d blob=%p", ap.Ctot, Cout, KH, KW, stride, M, tc_bn, (const void*)w_tc);
     }
     return launch_igemm(ap, w_packed, ldw, K, M, ep, to_stream(s));
 }
@@ -350,7 +351,10 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     Epilogue e1{nullptr, b_om, nullptr, 0, om, 32, 32, 0};
     int rc = DEFT_EINVAL;
     if (flags & DEFT_FLAG_TENSORCORE) rc = tc_conv_dispatch(cap, w_om_tc, om_bn, 32, 9 * Cin, M, e1, flags & ~DEFT_FLAG_TF32X1, scratch, scratch_bytes, to_stream(s));
-    if (rc == DEFT_EINVAL) rc = launch_igemm(cap, w_om_packed, 32, 9 * Cin, M, e1, to_stream(s));
+    if (rc == DEFT_EINVAL) {
+        if (flags & DEFT_FLAG_TENSORCORE) note_simt_fallback("deft_dcnv2_forward(offset conv)", "Cin=%d M=%d bn=%d", Cin, M, om_bn);
+        rc = launch_igemm(cap, w_om_packed, 32, 9 * Cin, M, e1, to_stream(s));
+    }
     if (rc != DEFT_OK) return rc;
     // 2) deformable gather fused into the GEMM's A producer
     DcnAP dap{};
@@ -359,6 +363,7 @@ int deft_dcnv2_forward(const float* x, int x_pitch, int N, int H, int W, int Cin
     if (flags & DEFT_FLAG_TENSORCORE) {
         rc = tc_dcn_dispatch(dap, w_tc, tc_bn, ldw, 9 * Cin, M, e2, flags, scratch, scratch_bytes, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;
+        note_simt_fallback("deft_dcnv2_forward(gather GEMM)", "Cin=%d Cout=%d M=%d bn=%d", Cin, Cout, M, tc_bn);
     }
     return launch_igemm(dap, w_packed, ldw, 9 * Cin, M, e2, to_stream(s));
 }
@@ -406,6 +411,7 @@ int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, i
         for (int h = 0; h < nheads; ++h) { ha.out[h] = ho.out[h]; ha.c[h] = ho.c[h]; ha.row0[h] = ho.row0[h]; }
         int rc = tc_heads_dispatch(cap, w1_tc, 9 * Cin, M, ha, flags, to_stream(s));
         if (rc != DEFT_EINVAL) return rc;
+        note_simt_fallback("deft_heads_forward", "Cin=%d nheads=%d M=%d", Cin, nheads, M);
     }
     if (ws_bytes < deft_heads_workspace_bytes(N, H, W, nheads, head_conv)) {   // only the unfused path needs the hidden map
         set_error("heads: workspace too small");
@@ -416,11 +422,8 @@ int deft_heads_forward(const float* feat, int feat_pitch, int N, int H, int W, i
     if (rc != DEFT_OK) return rc;
     size_t smem = ((size_t)row * head_conv + (size_t)row * 32) * sizeof(float);
     DEFT_REQUIRE(smem <= 200 * 1024, "heads: too many output channels (%d)", row);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(heads1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-    }
+    static size_t granted[DEFT_MAX_DEVICES] = {};
+    if ((rc = ensure_dyn_smem(heads1x1_kernel, smem, granted, "heads1x1")) != DEFT_OK) return rc;
     heads1x1_kernel<<<ceil_div(M, 32), 256, smem, to_stream(s)>>>(hidden, HCt, head_conv, w2, b2, ho, H * W, M);
     DEFT_CHECK_LAUNCH("heads1x1");
     return DEFT_OK;

@@ -190,25 +190,33 @@ __global__ void affinity_final_kernel(const float* __restrict__ h4, const float*
 struct SoftmaxArgs {
     int n[AFF_MAX_FRAMES];
     int off[AFF_MAX_FRAMES + 1];
-    int m, P;
+    const int* n_dev;    // [F] live rows per memory frame on the device (overrides n[]) or nullptr
+    const int* m_dev;    // live current detections on the device (overrides m) or nullptr
+    int m, ms, P;        // m: live columns; ms: row stride of S (the pair grid's column count)
 };
 // One block per memory frame.  X = [[S (n x m), 0...; 0...], ones row/col] of size (P+1)^2 as in
 // AFE.py:123-134; rows/cols beyond n/m are exact zeros and enter the denominators analytically.
+// The whole [P, P+1] block of `out` is written (zeros outside the live [n, m+1] corner), so a reused buffer never
+// shows values of an earlier, larger frame.
 __global__ void __launch_bounds__(256) affinity_softmax_kernel(const float* __restrict__ S, SoftmaxArgs a, float* __restrict__ out) {
     DEFT_PDL_PROLOGUE();
     extern __shared__ float sm[];
-    const int P = a.P, m = a.m, f = blockIdx.x, n = a.n[f];
+    const int P = a.P, ms = a.ms, f = blockIdx.x;
+    int m = a.m_dev ? __ldg(a.m_dev) : a.m;
+    int n = a.n_dev ? __ldg(a.n_dev + f) : a.n[f];
+    m = min(max(m, 0), min(ms, P));
+    n = min(max(n, 0), P);
     float* rmax = sm; float* rsum = sm + P; float* cmax = sm + 2 * P; float* csum = sm + 3 * P;
     const float* Sf = S + a.off[f];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = warp; i < n; i += 8) {
         float mx = 1.0f;                       // the appended false-object column
         if (m < P) mx = fmaxf(mx, 0.f);
-        for (int j = lane; j < m; j += 32) mx = fmaxf(mx, Sf[i * m + j]);
+        for (int j = lane; j < m; j += 32) mx = fmaxf(mx, Sf[i * ms + j]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         float s = 0.f;
-        for (int j = lane; j < m; j += 32) s += expf(Sf[i * m + j] - mx);
+        for (int j = lane; j < m; j += 32) s += expf(Sf[i * ms + j] - mx);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) { rmax[i] = mx; rsum[i] = s + (float)(P - m) * expf(0.f - mx) + expf(1.0f - mx); }
@@ -216,24 +224,35 @@ __global__ void __launch_bounds__(256) affinity_softmax_kernel(const float* __re
     for (int j = tid; j < m; j += 256) {
         float mx = 1.0f;
         if (n < P) mx = fmaxf(mx, 0.f);
-        for (int i = 0; i < n; ++i) mx = fmaxf(mx, Sf[i * m + j]);
+        for (int i = 0; i < n; ++i) mx = fmaxf(mx, Sf[i * ms + j]);
         float s = 0.f;
-        for (int i = 0; i < n; ++i) s += expf(Sf[i * m + j] - mx);
+        for (int i = 0; i < n; ++i) s += expf(Sf[i * ms + j] - mx);
         cmax[j] = mx;
         csum[j] = s + (float)(P - n) * expf(0.f - mx) + expf(1.0f - mx);
     }
     __syncthreads();
     float* of = out + (size_t)f * P * (P + 1);
-    for (int idx = tid; idx < n * (m + 1); idx += 256) {
-        int i = idx / (m + 1), j = idx - i * (m + 1);
-        float v;
-        if (j < m) {
-            float s = Sf[i * m + j];
+    for (int idx = tid; idx < P * (P + 1); idx += 256) {
+        int i = idx / (P + 1), j = idx - i * (P + 1);
+        float v = 0.f;
+        if (i < n && j < m) {
+            float s = Sf[i * ms + j];
             v = fmaxf(expf(s - rmax[i]) / rsum[i], expf(s - cmax[j]) / csum[j]);
-        } else {
+        } else if (i < n && j == m) {
             v = expf(1.0f - rmax[i]) / rsum[i];
         }
-        of[(size_t)i * (P + 1) + j] = v;
+        of[idx] = v;
+    }
+}
+
+// a9 (AFE.py:74-86 + add_unmatched_dim 215-233): the raw score matrix of every batch element with the false-object
+// column and row of ones appended: out[b] = [[S_b (P x P), 1], [1 ... 1]]  ((P+1)^2, no softmax, no zeroing).
+__global__ void affinity_scores_kernel(const float* __restrict__ S, int P, float false_constant, float* __restrict__ out) {
+    DEFT_PDL_PROLOGUE();
+    const int b = blockIdx.y, Q = P + 1;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Q * Q; idx += gridDim.x * blockDim.x) {
+        int i = idx / Q, j = idx - i * Q;
+        out[(size_t)b * Q * Q + idx] = (i < P && j < P) ? S[(size_t)b * P * P + i * P + j] : false_constant;
     }
 }
 
@@ -248,6 +267,7 @@ __global__ void __launch_bounds__(128) lstm_step_kernel(const float* __restrict_
     __shared__ float gates[512];
     __shared__ __align__(16) float hn[128];
     __shared__ __align__(16) float o1[64];
+    DEFT_PDL_PROLOGUE();
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float4 hv = ldg4(h + (size_t)t * 128 + lane * 4);
     const float xv = (lane < F) ? x[(size_t)t * F + lane] : 0.f;
@@ -331,20 +351,15 @@ int deft_decode(const float* hm, int B, int C, int H, int W, int K, const float*
         reinterpret_cast<char*>(ws) + align_up((size_t)B * C * nchunks * K * sizeof(unsigned long long), 256));
     launch_pdl(topk_chunk_kernel, dim3(nchunks, C, B), dim3(1024), 0, to_stream(s), hm, H, W, K, nchunks, cand_chunk);
     DEFT_CHECK_LAUNCH("topk_chunk");
-    static size_t attr_b = 48 * 1024, attr_c = 48 * 1024;
+    static size_t granted_b[DEFT_MAX_DEVICES] = {}, granted_c[DEFT_MAX_DEVICES] = {};
     size_t smem_b = (size_t)Mp * sizeof(unsigned long long);
-    if (smem_b > attr_b) {
-        cudaFuncSetAttribute(topk_class_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-        attr_b = smem_b;
-    }
+    int rc_attr = ensure_dyn_smem(topk_class_merge_kernel, smem_b, granted_b, "topk_class_merge");
+    if (rc_attr != DEFT_OK) return rc_attr;
     launch_pdl(topk_class_merge_kernel, dim3(C, B), dim3(1024), smem_b, to_stream(s), cand_chunk, nchunks * K, Mp, K, cand);
     DEFT_CHECK_LAUNCH("topk_class_merge");
     DecodeArgs a{cand, reg, wh, ltrb_amodal, scores, (long long*)inds, clses, ys, xs, bboxes, bboxes_amodal, C, H, W, K};
     size_t smem = (size_t)Np * sizeof(unsigned long long);
-    if (smem > attr_c) {
-        cudaFuncSetAttribute(decode_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_c = smem;
-    }
+    if ((rc_attr = ensure_dyn_smem(decode_merge_kernel, smem, granted_c, "decode_merge")) != DEFT_OK) return rc_attr;
     launch_pdl(decode_merge_kernel, dim3(B), dim3(1024), smem, to_stream(s), a, Np);
     DEFT_CHECK_LAUNCH("decode_merge");
     return DEFT_OK;
@@ -365,22 +380,30 @@ int deft_boxes_to_centres(const float* boxes, int N, float W, float H, float* ce
     return DEFT_OK;
 }
 
-static void affinity_ws_layout(int F, int P, size_t* o_au, size_t* o_bv, size_t* o_h2, size_t* o_h3, size_t* o_h4, size_t* o_s, size_t* total) {
-    size_t pairs = (size_t)F * P * P, off = 0;
-    *o_au = off; off += align_up((size_t)F * P * 512 * 4, 256);
-    *o_bv = off; off += align_up((size_t)P * 512 * 4, 256);
-    *o_h2 = off; off += align_up(pairs * 256 * 4, 256);
-    *o_h3 = off; off += align_up(pairs * 128 * 4, 256);
-    *o_h4 = off; off += align_up(pairs * 64 * 4, 256);
-    *o_s = off; off += align_up(pairs * 4, 256);
-    *total = off;
+struct AffinityWs { float *au, *bv, *h2, *h3, *h4, *S; size_t total; };
+// pairs = rows of the pair grid; au_rows / bv_rows = rows of the projected first-layer halves kept in the workspace
+// (0 when the caller supplies them: cached Au' of the memory ring, deft_afe_project output).
+static AffinityWs affinity_ws_layout(void* base, size_t pairs, size_t au_rows, size_t bv_rows) {
+    AffinityWs w{};
+    size_t off = 0;
+    char* b = reinterpret_cast<char*>(base);
+    auto take = [&](size_t bytes) { float* p = reinterpret_cast<float*>(b + off); off += align_up(bytes, 256); return p; };
+    w.au = take(au_rows * 512 * 4);
+    w.bv = take(bv_rows * 512 * 4);
+    w.h2 = take(pairs * 256 * 4);
+    w.h3 = take(pairs * 128 * 4);
+    w.h4 = take(pairs * 64 * 4);
+    w.S = take(pairs * 4);
+    w.total = off;
+    return w;
 }
 
 size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb) {
     (void)Cemb;
-    size_t a, b, c, d, e, f, t;
-    affinity_ws_layout(F, P, &a, &b, &c, &d, &e, &f, &t);
-    return t;
+    return affinity_ws_layout(nullptr, (size_t)F * P * P, (size_t)F * P, (size_t)P).total;
+}
+size_t deft_afe_pairs_workspace_bytes(int F, int rows, int cols) {
+    return affinity_ws_layout(nullptr, (size_t)F * rows * cols, 0, 0).total;
 }
 
 static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp, const float* Wtc, int tcbn, int ldw, const float* sc, const float* sh,
@@ -392,8 +415,50 @@ static int plain_gemm(const float* A, int lda, int Mrows, int K, const float* Wp
     if (flags & DEFT_FLAG_TENSORCORE) {
         int rc = tc_conv_dispatch(ap, Wtc, tcbn, ldw, K, Mrows, ep, flags, nullptr, 0, st);
         if (rc != DEFT_EINVAL) return rc;
+        note_simt_fallback("deft_afe_affinity(gemm)", "K=%d ldw=%d M=%d bn=%d", K, ldw, Mrows, tcbn);
     }
     return launch_igemm(ap, Wp, ldw, K, Mrows, ep, st);
+}
+
+// Layers 2..5 of the pairwise MLP (AFE.py:331-347 after the decomposed first layer) over the M pair rows `pap` describes:
+// relu(Au'_i + Bv'_j) -> 256 -> 128 -> 64 -> relu(dot) = S[M].
+struct AffinityMlp {
+    const float *w2, *sc2, *sh2, *w3, *sc3, *sh3, *w4, *b4, *w5;
+    float b5;
+    const float *t2, *t3, *t4;
+    int bn2, bn3, bn4;
+};
+static int affinity_mlp(const PairAP& pap, int M, const AffinityMlp& w, const AffinityWs& ws, unsigned flags, cudaStream_t st) {
+    Epilogue e2{w.sc2, w.sh2, nullptr, 0, ws.h2, 256, 256, 1};
+    int rc = DEFT_EINVAL;
+    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_pair_dispatch(pap, w.t2, w.bn2, 256, 512, M, e2, flags, st);
+    if (rc == DEFT_EINVAL) {
+        if (flags & DEFT_FLAG_TENSORCORE) note_simt_fallback("deft_afe_affinity(pair GEMM)", "M=%d bn=%d", M, w.bn2);
+        rc = launch_igemm(pap, w.w2, 256, 512, M, e2, st);
+    }
+    if (rc != DEFT_OK) return rc;
+    if ((rc = plain_gemm(ws.h2, 256, M, 256, w.w3, w.t3, w.bn3, 128, w.sc3, w.sh3, ws.h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
+    if ((rc = plain_gemm(ws.h3, 128, M, 128, w.w4, w.t4, w.bn4, 64, nullptr, w.b4, ws.h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
+    launch_pdl(affinity_final_kernel, dim3(ceil_div(M, 32)), dim3(256), 0, st, (const float*)ws.h4, w.w5, w.b5, ws.S, M);
+    DEFT_CHECK_LAUNCH("affinity_final");
+    return DEFT_OK;
+}
+static AffinityMlp make_mlp(const float* w2, const float* sc2, const float* sh2, const float* w3, const float* sc3, const float* sh3, const float* w4,
+                            const float* b4, const float* w5, float b5, const float* const* tc, const int* tcbn) {
+    AffinityMlp w{w2, sc2, sh2, w3, sc3, sh3, w4, b4, w5, b5, nullptr, nullptr, nullptr, 0, 0, 0};
+    if (tc && tcbn) { w.t2 = tc[2]; w.t3 = tc[3]; w.t4 = tc[4]; w.bn2 = tcbn[2]; w.bn3 = tcbn[3]; w.bn4 = tcbn[4]; }
+    return w;
+}
+
+int deft_afe_project(const float* emb, int rows, int Cemb, const float* w1a, const float* w1b, const float* sh1, const float* const* tc,
+                     const int* tcbn, float* au, float* bv, unsigned flags, deft_stream_t s) {
+    DEFT_REQUIRE(emb && w1a && w1b && sh1 && (au || bv) && rows >= 1 && Cemb % 16 == 0, "afe_project: bad args");
+    cudaStream_t st = to_stream(s);
+    const unsigned fl = flags & ~DEFT_FLAG_TF32X1;
+    int rc;
+    if (au && (rc = plain_gemm(emb, Cemb, rows, Cemb, w1a, tc ? tc[0] : nullptr, tcbn ? tcbn[0] : 0, 512, nullptr, sh1, au, 512, 512, 0, fl, st)) != DEFT_OK) return rc;
+    if (bv && (rc = plain_gemm(emb, Cemb, rows, Cemb, w1b, tc ? tc[1] : nullptr, tcbn ? tcbn[1] : 0, 512, nullptr, nullptr, bv, 512, 512, 0, fl, st)) != DEFT_OK) return rc;
+    return DEFT_OK;
 }
 
 int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb, const float* w1a,
@@ -404,12 +469,8 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
     DEFT_REQUIRE(xp && n_host && xn && out && ws && w1a && w1b && sh1 && w2 && w3 && w4 && w5, "afe_affinity: null argument");
     DEFT_REQUIRE(F >= 1 && F <= AFF_MAX_FRAMES && m >= 1 && m <= P && P <= 1024 && Cemb % 16 == 0,
                  "afe_affinity: need 1<=F<=%d, 1<=m<=P<=1024, Cemb%%16==0", AFF_MAX_FRAMES);
-    size_t o_au, o_bv, o_h2, o_h3, o_h4, o_s, total;
-    affinity_ws_layout(F, P, &o_au, &o_bv, &o_h2, &o_h3, &o_h4, &o_s, &total);
-    if (ws_bytes < total) { set_error("afe_affinity: workspace too small"); return DEFT_EWORKSPACE; }
-    char* base = reinterpret_cast<char*>(ws);
-    float* au = (float*)(base + o_au); float* bv = (float*)(base + o_bv); float* h2 = (float*)(base + o_h2);
-    float* h3 = (float*)(base + o_h3); float* h4 = (float*)(base + o_h4); float* S = (float*)(base + o_s);
+    if (ws_bytes < deft_afe_affinity_workspace_bytes(F, P, Cemb)) { set_error("afe_affinity: workspace too small"); return DEFT_EWORKSPACE; }
+    const AffinityWs w = affinity_ws_layout(ws, (size_t)F * P * P, (size_t)F * P, (size_t)P);
     cudaStream_t st = to_stream(s);
     PairAP pap{};
     SoftmaxArgs sa{};
@@ -420,29 +481,61 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
         M += n_host[f] * m;
     }
     pap.off[F] = M; sa.off[F] = M;
-    if (M == 0) return DEFT_OK;
+    sa.m = m; sa.ms = m; sa.P = P;
     int rc;
-    // layer 1, decomposed: Au' = bnfold(W1a u_i + b1), Bv' = bnfold-scale(W1b v_j)
-    const float* t1a = tc ? tc[0] : nullptr; const float* t1b = tc ? tc[1] : nullptr; const float* t2 = tc ? tc[2] : nullptr;
-    const float* t3 = tc ? tc[3] : nullptr; const float* t4 = tc ? tc[4] : nullptr;
-    int bn[5] = {0, 0, 0, 0, 0};
-    if (tc && tcbn) for (int i = 0; i < 5; ++i) bn[i] = tcbn[i];
-    if ((rc = plain_gemm(xp, Cemb, F * P, Cemb, w1a, t1a, bn[0], 512, nullptr, sh1, au, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(xn, Cemb, m, Cemb, w1b, t1b, bn[1], 512, nullptr, nullptr, bv, 512, 512, 0, flags & ~DEFT_FLAG_TF32X1, st)) != DEFT_OK) return rc;
-    // layer 2 with the pair expansion relu(Au'_i + Bv'_j) as the A producer
-    pap.au = au; pap.bv = bv; pap.P = P; pap.m = m; pap.F = F; pap.ld = 512;
-    Epilogue e2{sc2, sh2, nullptr, 0, h2, 256, 256, 1};
-    rc = DEFT_EINVAL;
-    if (flags & DEFT_FLAG_TENSORCORE) rc = tc_pair_dispatch(pap, t2, bn[2], 256, 512, M, e2, flags, st);
-    if (rc == DEFT_EINVAL) rc = launch_igemm(pap, w2, 256, 512, M, e2, st);
-    if (rc != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h2, 256, M, 256, w3, t3, bn[3], 128, sc3, sh3, h3, 128, 128, 1, flags, st)) != DEFT_OK) return rc;
-    if ((rc = plain_gemm(h3, 128, M, 128, w4, t4, bn[4], 64, nullptr, b4, h4, 64, 64, 1, flags, st)) != DEFT_OK) return rc;
-    launch_pdl(affinity_final_kernel, dim3(ceil_div(M, 32)), dim3(256), 0, st, h4, w5, b5, S, M);
-    DEFT_CHECK_LAUNCH("affinity_final");
-    sa.m = m; sa.P = P;
-    launch_pdl(affinity_softmax_kernel, dim3(F), dim3(256), 4 * P * sizeof(float), st, S, sa, out);
+    if (M > 0) {
+        // layer 1, decomposed: Au' = bnfold(W1a u_i + b1), Bv' = bnfold-scale(W1b v_j)
+        if ((rc = deft_afe_project(xp, F * P, Cemb, w1a, w1b, sh1, tc, tcbn, w.au, nullptr, flags, s)) != DEFT_OK) return rc;
+        if ((rc = deft_afe_project(xn, m, Cemb, w1a, w1b, sh1, tc, tcbn, nullptr, w.bv, flags, s)) != DEFT_OK) return rc;
+        pap.au = w.au; pap.bv = w.bv; pap.P = P; pap.m = m; pap.F = F; pap.ld = 512;
+        if ((rc = affinity_mlp(pap, M, make_mlp(w2, sc2, sh2, w3, sc3, sh3, w4, b4, w5, b5, tc, tcbn), w, flags, st)) != DEFT_OK) return rc;
+    }
+    // M == 0 (no live pair): the softmax kernel still clears the output blocks
+    launch_pdl(affinity_softmax_kernel, dim3(F), dim3(256), 4 * P * sizeof(float), st, (const float*)w.S, sa, out);
     DEFT_CHECK_LAUNCH("affinity_softmax");
+    return DEFT_OK;
+}
+
+int deft_afe_affinity_cached(const float* au_mem, int F, int P, int rows, const int* n_dev, const float* bv, int m_max, const int* m_dev,
+                             const float* w2, const float* sc2, const float* sh2, const float* w3, const float* sc3, const float* sh3,
+                             const float* w4, const float* b4, const float* w5, float b5, const float* const* tc, const int* tcbn,
+                             float* out, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s) {
+    DEFT_REQUIRE(au_mem && n_dev && bv && out && ws && w2 && w3 && w4 && w5, "afe_affinity_cached: null argument");
+    DEFT_REQUIRE(F >= 1 && F <= AFF_MAX_FRAMES && rows >= 1 && rows <= P && m_max >= 1 && m_max <= P && P <= 1024,
+                 "afe_affinity_cached: need 1<=F<=%d, 1<=rows<=P, 1<=m_max<=P<=1024", AFF_MAX_FRAMES);
+    if (ws_bytes < deft_afe_pairs_workspace_bytes(F, rows, m_max)) { set_error("afe_affinity_cached: workspace too small"); return DEFT_EWORKSPACE; }
+    const AffinityWs w = affinity_ws_layout(ws, (size_t)F * rows * m_max, 0, 0);
+    // uniform pair grid: frame f owns rows [f*rows*m_max, (f+1)*rows*m_max); rows >= n_dev[f] / columns >= *m_dev are
+    // computed (the live counts stay on the device, the launch is graph-capturable) and ignored by the softmax
+    PairAP pap{};
+    SoftmaxArgs sa{};
+    for (int f = 0; f <= F; ++f) { pap.off[f] = f * rows * m_max; sa.off[f] = pap.off[f]; }
+    pap.au = au_mem; pap.bv = bv; pap.P = P; pap.m = m_max; pap.F = F; pap.ld = 512;
+    sa.n_dev = n_dev; sa.m_dev = m_dev; sa.m = m_max; sa.ms = m_max; sa.P = P;
+    cudaStream_t st = to_stream(s);
+    int rc = affinity_mlp(pap, F * rows * m_max, make_mlp(w2, sc2, sh2, w3, sc3, sh3, w4, b4, w5, b5, tc, tcbn), w, flags, st);
+    if (rc != DEFT_OK) return rc;
+    launch_pdl(affinity_softmax_kernel, dim3(F), dim3(256), 4 * P * sizeof(float), st, (const float*)w.S, sa, out);
+    DEFT_CHECK_LAUNCH("affinity_softmax");
+    return DEFT_OK;
+}
+
+int deft_afe_forward_scores(const float* au, const float* bv, int B, int P, const float* w2, const float* sc2, const float* sh2,
+                            const float* w3, const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5,
+                            const float* const* tc, const int* tcbn, float false_constant, float* out, unsigned flags, void* ws, size_t ws_bytes,
+                            deft_stream_t s) {
+    DEFT_REQUIRE(au && bv && out && ws && w2 && w3 && w4 && w5, "afe_forward_scores: null argument");
+    DEFT_REQUIRE(B >= 1 && B <= AFF_MAX_FRAMES && P >= 1 && P <= 1024, "afe_forward_scores: need 1<=B<=%d, 1<=P<=1024", AFF_MAX_FRAMES);
+    if (ws_bytes < deft_afe_pairs_workspace_bytes(B, P, P)) { set_error("afe_forward_scores: workspace too small"); return DEFT_EWORKSPACE; }
+    const AffinityWs w = affinity_ws_layout(ws, (size_t)B * P * P, 0, 0);
+    PairAP pap{};
+    for (int f = 0; f <= B; ++f) pap.off[f] = f * P * P;
+    pap.au = au; pap.bv = bv; pap.P = P; pap.m = P; pap.F = B; pap.ld = 512; pap.bvf = (long long)P * 512;
+    cudaStream_t st = to_stream(s);
+    int rc = affinity_mlp(pap, B * P * P, make_mlp(w2, sc2, sh2, w3, sc3, sh3, w4, b4, w5, b5, tc, tcbn), w, flags, st);
+    if (rc != DEFT_OK) return rc;
+    launch_pdl(affinity_scores_kernel, dim3(ceil_div((P + 1) * (P + 1), 256), B), dim3(256), 0, st, (const float*)w.S, P, false_constant, out);
+    DEFT_CHECK_LAUNCH("affinity_scores");
     return DEFT_OK;
 }
 
@@ -451,7 +544,7 @@ int deft_lstm_step(const float* x, const float* h, const float* c, const float* 
                    float* h_out, float* c_out, float* pred, deft_stream_t s) {
     DEFT_REQUIRE(x && h && c && w_ih && w_hh && b_ih && b_hh && w1 && b1 && w2 && b2 && h_out && c_out && pred, "lstm_step: null argument");
     DEFT_REQUIRE(T >= 1 && F >= 1 && F <= 32 && nout >= 1 && nout <= 64, "lstm_step: need F<=32, nout<=64 (F=%d nout=%d)", F, nout);
-    lstm_step_kernel<<<T, 128, 0, to_stream(s)>>>(x, h, c, w_ih, w_hh, b_ih, b_hh, w1, b1, w2, b2, F, nout, h_out, c_out, pred);
+    launch_pdl(lstm_step_kernel, dim3(T), dim3(128), 0, to_stream(s), x, h, c, w_ih, w_hh, b_ih, b_hh, w1, b1, w2, b2, F, nout, h_out, c_out, pred);
     DEFT_CHECK_LAUNCH("lstm_step");
     return DEFT_OK;
 }

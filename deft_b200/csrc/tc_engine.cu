@@ -384,7 +384,7 @@ struct TcPairAP {
                 int q = p - a.off[f];
                 int ii = q / a.m, jj = q - ii * a.m;
                 pa_[i] = a.au + ((size_t)f * a.P + ii) * a.ld;
-                pb_[i] = a.bv + (size_t)jj * a.ld;
+                pb_[i] = a.bv + (size_t)f * a.bvf + (size_t)jj * a.ld;
             }
         }
     }
@@ -836,7 +836,11 @@ int tc_k_perm_taps(int K, int taps) { return (taps > 1 && K % taps == 0 && (K / 
 
 int tc_pick_bn(int ldw, int M, int kind) {
     if (kind == TC_KIND_HEADS) return 256;
-    const int max_bn = (kind == TC_KIND_DCN) ? 64 : 128;
+    // DCN: the bilinear gather is the expensive side, so every gathered A tile should meet all of Cout (up to 128 columns;
+    // r1 capped this at 64 and repeated the gather 2x / 4x for the Cout = 128 / 256 layers).  DEFT_DCN_MAXBN overrides.
+    static int dcn_max = -1;
+    if (dcn_max < 0) { const char* e = getenv("DEFT_DCN_MAXBN"); dcn_max = e ? atoi(e) : 128; if (dcn_max != 32 && dcn_max != 64) dcn_max = 128; }
+    const int max_bn = (kind == TC_KIND_DCN) ? dcn_max : 128;
     const int mt = ceil_div(M, TC_BM);
     int best = 0;
     // DEFT_TC_WIDE=1 (default): always the widest dividing tile -- with several frames in flight (FramePipeline) idle SMs
@@ -893,20 +897,18 @@ static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int 
     if (stages > 6) stages = 6;
     if (stages < 2) return DEFT_EINVAL;
     size_t smem = (size_t)stages * STAGE_BYTES + fixed;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(tc_igemm_kernel<AP, BN, NPASS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
-            set_error("tc_engine: cannot raise dynamic smem limit");
-            return DEFT_ECUDA;
-        }
-        attr_done = true;
+    static size_t granted[DEFT_MAX_DEVICES] = {};
+    {
+        const int rc_attr = ensure_dyn_smem(tc_igemm_kernel<AP, BN, NPASS, EPI>, TC_SMEM_LIMIT, granted, "tc_igemm_kernel");
+        if (rc_attr != DEFT_OK) return rc_attr;
     }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("DEFT_TC_DBG"); dbg = e ? atoi(e) : 0; }
-    if (const char* e = getenv("DEFT_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) { stages = v; } }
+    static int stage_cap = -1;
+    if (stage_cap < 0) { const char* e = getenv("DEFT_TC_STAGES"); stage_cap = e ? atoi(e) : 0; }
+    if (stage_cap >= 2 && stage_cap < stages) stages = stage_cap;
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
-    long long* trace = nullptr;
-    if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
+    long long* trace = debug_trace_ptr();
     launch_pdl(tc_igemm_kernel<AP, BN, NPASS, EPI>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, stages, epi, dbg, trace);
     DEFT_CHECK_LAUNCH("tc_igemm_kernel");
     return DEFT_OK;
@@ -1088,7 +1090,7 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
 
 int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                     size_t scratch_bytes, cudaStream_t st) {
-    if (ap.Cin % 32 != 0 || bn > 64) return DEFT_EINVAL;
+    if (ap.Cin % 32 != 0 || bn > 128) return DEFT_EINVAL;
     static int ts_dcn = -1;
     if (ts_dcn < 0) { const char* e = getenv("DEFT_TC_TS_DCN"); ts_dcn = e ? atoi(e) : 1; }
     if (ts_dcn && ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {

@@ -112,24 +112,32 @@ struct TsConvAP {
     }
 };
 
-// DCNv2 bilinear gather; K order = (32-channel block, tap, channel).  The 4 corner element-offsets / weights of the
-// tile's 128 rows x 9 taps live in smem (built once per tile by all producers).
+// DCNv2 bilinear gather; K order = (32-channel block, tap, channel).  The corner table of the tile's 128 rows x 9 taps
+// lives in smem (built once per tile by all producers), 20 bytes per (row, tap):
+//   tabB: element offset of the clamped top-left corner (a multiple of 4) | dx | dy << 1   (dx, dy: 1 = the right /
+//         lower neighbour exists, 0 = it coincides with the clamped corner and carries zero weight or IS that row/col)
+//   tabW: {wy0, wy1, wx0, wx1} with the validity of each corner row / column and the sigmoid mask folded in:
+//         w(corner y, corner x) = wy * wx.
+// Compact on purpose: the gather runs through L1, and every KB of shared memory the CTA does not claim is L1
+// (r1 ncu: 56 % L1 hit rate with 225 KB of smem configured; the corner neighbourhood of a tile is ~27 KB per
+// channel block).
 struct TsDcnAP {
     static constexpr bool kPatch = false;
     DcnAP a;
-    static constexpr int kExtraSmemBytes = TC_BM * 9 * 32;
-    const int4* tabO_;
+    static constexpr int kExtraSmemBytes = TC_BM * 9 * 20;
+    const int* tabB_;
     const float4* tabW_;
+    int rowpitch_;
     __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void tile_init(int m0, int M, unsigned char* extra, int, int, int4*) {
-        int4* tabO = reinterpret_cast<int4*>(extra);
-        float4* tabW = reinterpret_cast<float4*>(extra + TC_BM * 9 * 16);
+        float4* tabW = reinterpret_cast<float4*>(extra);
+        int* tabB = reinterpret_cast<int*>(extra + TC_BM * 9 * 16);
         const int H = a.H, W = a.W;
         asm volatile("bar.sync 1, 512;" ::: "memory");     // every producer is done with the previous tile's table
         for (int idx = threadIdx.x; idx < TC_BM * 9; idx += TC_PRODUCERS) {
             int r9 = idx / 9, tap = idx - r9 * 9;
             int p = m0 + r9;
-            int4 o = make_int4(0, 0, 0, 0);
+            int code = 0;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p < M) {
                 int n = p / (H * W);
@@ -145,37 +153,46 @@ struct TsDcnAP {
                     float fy = floorf(py), fx = floorf(px);
                     int y0 = (int)fy, x0 = (int)fx;
                     float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
-                    int base = n * H * W;
-                    bool y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1;
-                    if (y0ok && x0ok) { o.x = (base + y0 * W + x0) * a.pitch; w.x = hy * hx * mk; }
-                    if (y0ok && x1ok) { o.y = (base + y0 * W + x0 + 1) * a.pitch; w.y = hy * lx * mk; }
-                    if (y1ok && x0ok) { o.z = (base + (y0 + 1) * W + x0) * a.pitch; w.z = ly * hx * mk; }
-                    if (y1ok && x1ok) { o.w = (base + (y0 + 1) * W + x0 + 1) * a.pitch; w.w = ly * lx * mk; }
+                    const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1;
+                    w.x = y0ok ? hy : 0.f;
+                    w.y = y1ok ? ly : 0.f;
+                    w.z = x0ok ? hx * mk : 0.f;
+                    w.w = x1ok ? lx * mk : 0.f;
+                    const int yc = y0ok ? y0 : 0, xc = x0ok ? x0 : 0;     // y0 = -1: the lower row IS row 0 (dy = 0)
+                    code = ((n * H + yc) * W + xc) * a.pitch | ((x0ok && x1ok) ? 1 : 0) | ((y0ok && y1ok) ? 2 : 0);
                 }
             }
-            tabO[idx] = o;       // element offsets; corners with zero weight point at element 0 (a valid address)
+            tabB[idx] = code;    // all-zero weights point at element 0: always a valid address
             tabW[idx] = w;
         }
-        tabO_ = tabO;
+        tabB_ = tabB;
         tabW_ = tabW;
+        rowpitch_ = W * a.pitch;
         asm volatile("bar.sync 1, 512;" ::: "memory");
     }
     __device__ __forceinline__ void fill(int kb, int quad, int lane, const int4*, float* stage) const {
         const int cb = kb / 9, tap = kb - cb * 9;
         const int ch = (lane & 7) * 4;
         const float* x = a.x + cb * TC_BK + ch;
+        const int pitch = a.pitch, rowpitch = rowpitch_;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {                   // two rows (8 corner loads) in flight at a time
             const int r0 = (lane >> 3) + 8 * jj, r1 = r0 + 4;
-            const int4 o0 = tabO_[(quad * 32 + r0) * 9 + tap], o1 = tabO_[(quad * 32 + r1) * 9 + tap];
+            const int c0 = tabB_[(quad * 32 + r0) * 9 + tap], c1 = tabB_[(quad * 32 + r1) * 9 + tap];
             const float4 w0 = tabW_[(quad * 32 + r0) * 9 + tap], w1 = tabW_[(quad * 32 + r1) * 9 + tap];
-            const float4 a0 = ldg4(x + o0.x), a1 = ldg4(x + o0.y), a2 = ldg4(x + o0.z), a3 = ldg4(x + o0.w);
-            const float4 b0 = ldg4(x + o1.x), b1 = ldg4(x + o1.y), b2 = ldg4(x + o1.z), b3 = ldg4(x + o1.w);
+            const float* p0 = x + (c0 & ~3);
+            const float* p1 = x + (c1 & ~3);
+            const int dx0 = (c0 & 1) ? pitch : 0, dy0 = (c0 & 2) ? rowpitch : 0;
+            const int dx1 = (c1 & 1) ? pitch : 0, dy1 = (c1 & 2) ? rowpitch : 0;
+            const float4 a0 = ldg4(p0), a1 = ldg4(p0 + dx0), a2 = ldg4(p0 + dy0), a3 = ldg4(p0 + dy0 + dx0);
+            const float4 b0 = ldg4(p1), b1 = ldg4(p1 + dx1), b2 = ldg4(p1 + dy1), b3 = ldg4(p1 + dy1 + dx1);
+            const float u00 = w0.x * w0.z, u01 = w0.x * w0.w, u10 = w0.y * w0.z, u11 = w0.y * w0.w;
+            const float v00 = w1.x * w1.z, v01 = w1.x * w1.w, v10 = w1.y * w1.z, v11 = w1.y * w1.w;
             float4 u, v;
-            u.x = w0.x * a0.x + w0.y * a1.x + w0.z * a2.x + w0.w * a3.x; u.y = w0.x * a0.y + w0.y * a1.y + w0.z * a2.y + w0.w * a3.y;
-            u.z = w0.x * a0.z + w0.y * a1.z + w0.z * a2.z + w0.w * a3.z; u.w = w0.x * a0.w + w0.y * a1.w + w0.z * a2.w + w0.w * a3.w;
-            v.x = w1.x * b0.x + w1.y * b1.x + w1.z * b2.x + w1.w * b3.x; v.y = w1.x * b0.y + w1.y * b1.y + w1.z * b2.y + w1.w * b3.y;
-            v.z = w1.x * b0.z + w1.y * b1.z + w1.z * b2.z + w1.w * b3.z; v.w = w1.x * b0.w + w1.y * b1.w + w1.z * b2.w + w1.w * b3.w;
+            u.x = u00 * a0.x + u01 * a1.x + u10 * a2.x + u11 * a3.x; u.y = u00 * a0.y + u01 * a1.y + u10 * a2.y + u11 * a3.y;
+            u.z = u00 * a0.z + u01 * a1.z + u10 * a2.z + u11 * a3.z; u.w = u00 * a0.w + u01 * a1.w + u10 * a2.w + u11 * a3.w;
+            v.x = v00 * b0.x + v01 * b1.x + v10 * b2.x + v11 * b3.x; v.y = v00 * b0.y + v01 * b1.y + v10 * b2.y + v11 * b3.y;
+            v.z = v00 * b0.z + v01 * b1.z + v10 * b2.z + v11 * b3.z; v.w = v00 * b0.w + v01 * b1.w + v10 * b2.w + v11 * b3.w;
             *reinterpret_cast<float4*>(stage + r0 * TS_STAGE_LD + ch) = u;
             *reinterpret_cast<float4*>(stage + r1 * TS_STAGE_LD + ch) = v;
         }
@@ -197,7 +214,7 @@ struct TsPairAP {
             int q = p - a.off[f];
             int ii = q / a.m, jj = q - ii * a.m;
             offa = ((long long)f * a.P + ii) * a.ld;
-            offb = (long long)jj * a.ld;
+            offb = (long long)f * a.bvf + (long long)jj * a.ld;
         }
         meta[lane] = make_int4((int)(offa & 0xffffffffLL), (int)(offa >> 32), (int)(offb & 0xffffffffLL), (int)(offb >> 32));
         __syncwarp();
@@ -262,12 +279,30 @@ constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across pro
 // which the two issuers' MMAs land is timing dependent and results stop being bit-identical run to run
 // (tests/test_gpu_frame.py::test_c2_full_size_properties caught exactly that).
 constexpr int TS_ISSUERS = 2;
+#ifndef DEFT_TS_PAIR32
+#define DEFT_TS_PAIR32 1     // 1 = the N = 32 instantiation issues [hi|lo] as one N = 64 MMA (see TsCfg::PAIR)
+#endif
+#ifndef DEFT_TS_ISS128
+#define DEFT_TS_ISS128 1      // issuer warps of the N = 128 instantiations (A/B builds: make EXTRA=-DDEFT_TS_ISS128=2 OUT=...)
+#endif
 
 template <int BN, int NPASS>
 struct TsCfg {
     static constexpr int ACOLS = NPASS == 3 ? 64 : 32;                 // TMEM columns of one A stage (hi [+ lo])
-    static constexpr int NBUF = (2 * TS_ISSUERS * BN <= 256) ? 2 : 1;   // accumulator sets (double-buffered across tiles when they fit)
-    static constexpr int A0 = NBUF * TS_ISSUERS * BN;                   // first A column (after the accumulators)
+    // Issuer warps.  N <= 64: two, alternating k-blocks (a 128x64x8 MMA executes in ~32 cycles but costs ~46 to issue, so
+    // one issuer leaves the pipe idle).  N = 128: ONE -- r2 trace (profiles/r2_tc_trace.md): the pipe already runs at
+    // its floor (766 cycles per k-block vs 12 x 64), what is lost is the epilogue, which with two private 128-column
+    // accumulators cannot be double-buffered; one issuer = one accumulator per tile = two sets in 256 columns.
+    static constexpr int ISS = BN >= 128 ? DEFT_TS_ISS128 : TS_ISSUERS;
+    // N = 32 (the DCN offset/mask convs), 3xTF32: a TS-mode MMA costs ~the same to issue at N = 32 as at N = 64, so the
+    // two products that share A_hi are issued as ONE N = 64 instruction against the stage's [B_hi ; B_lo] rows (they
+    // are contiguous and form a valid 64-row swizzled tile): 2 MMAs per k-step instead of 3.  The accumulator of an
+    // issuer is then 2 x BN columns ([hi*hi + lo*hi | hi*lo]) and the epilogue adds the column blocks.
+    static constexpr bool PAIR = (BN == 32 && NPASS == 3 && DEFT_TS_PAIR32);
+    static constexpr int ACCW = PAIR ? 2 * BN : BN;                     // accumulator columns of one issuer
+    static constexpr int NBLK = (PAIR ? 2 : 1);                         // BN-wide column blocks per issuer
+    static constexpr int NBUF = (2 * ISS * ACCW <= 256) ? 2 : 1;        // accumulator sets (double-buffered across tiles when they fit)
+    static constexpr int A0 = NBUF * ISS * ACCW;                        // first A column (after the accumulators)
     static constexpr int SA_RAW = (512 - A0) / ACOLS;
     static constexpr int SA = SA_RAW > 6 ? 6 : SA_RAW;                  // A ring depth
     static constexpr int B_TILE = BN * 128;
@@ -291,8 +326,8 @@ struct TsRowMap {                                                   // accumulat
     }
 };
 template <int BN>
-__device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc, uint32_t acc2_cols, int ewarp, int lane, const TsRowMap& rm, int ntile,
-                                            int z, float* stage, const float* ss) {
+__device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc, int nblk, int ewarp, int lane, const TsRowMap& rm, int ntile,
+                                            int z, float* stage, const float* ss) {   // nblk consecutive BN-wide partial accumulators are added in order
     const Epilogue& e = epi.e;
     constexpr int LW = BN >= 32 ? 32 : BN;
     constexpr int LPR = LW / 4;                                     // lanes per row in the coalesced mapping
@@ -307,9 +342,10 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
         for (int h = 0; h < LW; h += LH) {
             float v[LH];
             tmem_ld<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), v);
-            if (acc2_cols) {                                        // the second issuer's accumulator, added in a fixed order
+#pragma unroll 1
+            for (int q = 1; q < nblk; ++q) {                        // the other partial accumulators, added in a fixed order
                 float v2[LH];
-                tmem_ld<LH>(tmem_acc + acc2_cols + lane_addr + (uint32_t)(c + h), v2);
+                tmem_ld<LH>(tmem_acc + (uint32_t)(q * BN) + lane_addr + (uint32_t)(c + h), v2);
 #pragma unroll
                 for (int j = 0; j < LH; ++j) v[j] += v2[j];
             }
@@ -401,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             mbar_init(b_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(acc_full(b), TS_ISSUERS);           // one commit (or plain arrive) per issuer warp
+            mbar_init(acc_full(b), Cfg::ISS);             // one commit (or plain arrive) per issuer warp
             mbar_init(acc_empty(b), TC_EWARPS);
         }
         for (int s = 0; s < TP_MAX_STAGES; ++s) {
@@ -578,7 +614,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
             // issuer 1's accumulator holds a partial sum only when the tile has >= 2 k-blocks
-            const uint32_t acc2 = (TS_ISSUERS > 1 && nkb > 1) ? (uint32_t)BN : 0u;
+            const int nblk = ((Cfg::ISS > 1 && nkb > 1) ? Cfg::ISS : 1) * Cfg::NBLK;
             TsRowMap rm{};
             rm.M = M;
             if constexpr (kPatch) {
@@ -590,7 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 rm.base = m0;                              // W = 0: rows are consecutive pixels
             }
             if (!(dbg & 16))
-                ts_epilogue<BN>(epi, tmem_base + (uint32_t)(b * TS_ISSUERS * BN), acc2, ewarp, lane, rm, ntile, z,
+                ts_epilogue<BN>(epi, tmem_base + (uint32_t)(b * Cfg::ISS * Cfg::ACCW), nblk, ewarp, lane, rm, ntile, z,
                                 reinterpret_cast<float*>(epi_stage) + ewarp * 32 * TS_EPI_LD, ss);
             tc_fence_before();
             __syncwarp();
@@ -604,7 +640,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
         constexpr uint32_t idesc = make_idesc(BN);
         const int w = warp - TC_MMA_WARP;
         int iter = 0, gk0 = 0;
-        for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
+        for (int t = (w < Cfg::ISS) ? (int)blockIdx.x : ts.total; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn;
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
@@ -612,8 +648,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const uint32_t tile_par = (uint32_t)(iter / Cfg::NBUF) & 1u;
             mbar_wait(acc_empty(b), tile_par ^ 1u, 4, iter);
             tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + (uint32_t)((b * TS_ISSUERS + w) * BN);
-            for (int i = w; i < nkb; i += TS_ISSUERS) {
+            const uint32_t tmem_acc = tmem_base + (uint32_t)((b * Cfg::ISS + w) * Cfg::ACCW);
+            for (int i = w; i < nkb; i += Cfg::ISS) {
                 const int gk = gk0 + i;
                 const int sa = gk % SA;
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
@@ -634,7 +670,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         if (dbg & 8) break;
                         const uint64_t db_hi = make_smem_desc(b_hi + k * 32);
-                        if (NPASS == 3) {
+                        if constexpr (Cfg::PAIR) {
+                            // A_hi x [B_hi ; B_lo] as one N = 2*BN MMA (initialises / accumulates both column blocks),
+                            // then the A_lo x B_hi correction into the first block
+                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, make_idesc(2 * BN), (i > w || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, 1u);
+                        } else if (NPASS == 3) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > w || k > 0) ? 1u : 0u);
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_lo, idesc, 1u);
@@ -645,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     }
                     umma_commit(a_empty(sa));
                     umma_commit(b_empty(s_b));
-                    if (i + TS_ISSUERS >= nkb) umma_commit(acc_full(b));     // this issuer's share of the tile is in flight
+                    if (i + Cfg::ISS >= nkb) umma_commit(acc_full(b));       // this issuer's share of the tile is in flight
                 }
                 __syncwarp();
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 3);
@@ -727,20 +768,34 @@ static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tile
     ts.total = ts.m_tiles * ts.n_tiles * ts.splits;
     int sb = (TC_SMEM_LIMIT - fixed) / Cfg::B_STAGE;
     if (sb > 8) sb = 8;
+    if (std::is_same<AP, TsDcnAP>::value) {
+        // The DCN gather goes through L1: claim only as much shared memory as the weight ring needs (DEFT_DCN_SB
+        // stages, default 3) so that the unified L1/smem array keeps >= 60 KB of cache for the corner neighbourhoods.
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("DEFT_DCN_SB"); cap = e ? atoi(e) : 3; if (cap < 2) cap = 2; }
+        if (sb > cap) sb = cap;
+    }
     if (sb < 2) return DEFT_EINVAL;
     size_t smem = (size_t)sb * Cfg::B_STAGE + fixed;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(tc_ts_kernel<AP, BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT) != cudaSuccess) {
-            set_error("tc_engine: cannot raise dynamic smem limit");
-            return DEFT_ECUDA;
+    static size_t granted[DEFT_MAX_DEVICES] = {};
+    {
+        const int rc_attr = ensure_dyn_smem(tc_ts_kernel<AP, BN, NPASS>, TC_SMEM_LIMIT, granted, "tc_ts_kernel");
+        if (rc_attr != DEFT_OK) return rc_attr;
+    }
+    if (std::is_same<AP, TsDcnAP>::value) {
+        // ask for exactly the shared memory this launch uses; the rest of the 256 KB array is the L1 the gather wants
+        static int carve_done[DEFT_MAX_DEVICES] = {};
+        int d = 0;
+        if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < DEFT_MAX_DEVICES && carve_done[d] != (int)smem) {
+            int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
+            if (pct > 100) pct = 100;
+            cudaFuncSetAttribute(tc_ts_kernel<AP, BN, NPASS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            carve_done[d] = (int)smem;
         }
-        attr_done = true;
     }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("DEFT_TC_DBG"); dbg = e ? atoi(e) : 0; }
-    long long* trace = nullptr;
-    if (const char* e = getenv("DEFT_TC_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
+    long long* trace = debug_trace_ptr();
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
     if (launch_pdl(tc_ts_kernel<AP, BN, NPASS>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, sb, ps, epi, dbg, trace) != cudaSuccess) {
         set_error("tc_ts_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));

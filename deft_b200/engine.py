@@ -17,7 +17,10 @@ from .ops import NHWC, FLAG_RELU
 
 
 class FramePlan:
-    def __init__(self, sd, heads, N, H, W, device, flags=0):
+    def __init__(self, sd, heads, N, H, W, device, flags=0, u8_norm=None):
+        """u8_norm = (mean[3], std[3]): the plan's input slot is a uint8 HWC frame [N,H,W,3] and the normalisation
+        (x/255 - mean)/std of detector.py:408-409 is fused into the stem's load; None: the
+        reference's pre-normalised fp32 NCHW image."""
         if H % 32 or W % 32:
             raise ValueError(f"DLASeg input must be a multiple of 32 (got {H}x{W}); pad like detector.py:370-371 does")
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point() else v for k, v in sd.items()}
@@ -26,7 +29,12 @@ class FramePlan:
         self.calls = []          # (cfunc, args-without-stream)
         self.keep = []           # packed weights / buffers kept alive
         self.graph = None
-        self.x_in = torch.empty((N, 3, H, W), dtype=torch.float32, device=device)
+        self.graph_pdl = None
+        self.u8_norm = None if u8_norm is None else (tuple(float(v) for v in u8_norm[0]), tuple(float(v) for v in u8_norm[1]))
+        if self.u8_norm is None:
+            self.x_in = torch.empty((N, 3, H, W), dtype=torch.float32, device=device)
+        else:
+            self.x_in = torch.empty((N, H, W, 3), dtype=torch.uint8, device=device)
         self._dcn_ws = None
         self._dcn_ws_bytes = 0
         self._build()
@@ -127,7 +135,13 @@ class FramePlan:
         sc, sh = packing.fold_bn(sd, "base.base_layer.1")
         self.keep += [wp, sc, sh]
         stem = self._buf(H, W, 16)
-        self._rec("deft_stem_conv7x7", self.x_in.data_ptr(), N, H, W, wp.data_ptr(), sc.data_ptr(), sh.data_ptr(), stem.ptr, stem.pitch)
+        if self.u8_norm is None:
+            self._rec("deft_stem_conv7x7", self.x_in.data_ptr(), N, H, W, wp.data_ptr(), sc.data_ptr(), sh.data_ptr(), stem.ptr, stem.pitch)
+        else:
+            mean_a, std_a = _lib.float_array(self.u8_norm[0]), _lib.float_array(self.u8_norm[1])
+            self.keep += [mean_a, std_a]
+            self._rec("deft_stem_conv7x7_u8", self.x_in.data_ptr(), N, H, W, mean_a, std_a, wp.data_ptr(), sc.data_ptr(), sh.data_ptr(), stem.ptr,
+                      stem.pitch, None)
         l0 = self._conv([stem], "base.level0.0.weight", "base.level0.1")
         l1 = self._conv([l0], "base.level1.0.weight", "base.level1.1", stride=2)
         l2 = self._tree1("base.level2", l1, 2, False, [])
@@ -172,25 +186,25 @@ class FramePlan:
 
     # ------------------------------------------------------------------ execution
     def launch(self):
-        s = _lib.stream_ptr()
-        for fn, args, name in self.calls:
-            rc = fn(*args, s)
-            if rc != 0:
-                _lib.check(rc, name)
+        with _lib.on_device(self.device) as s:          # the plan's device current; s = its current stream
+            for fn, args, name in self.calls:
+                rc = fn(*args, s)
+                if rc != 0:
+                    _lib.check(rc, name)
 
     def launch_profiled(self):
         """Eager launch with a CUDA-event pair around every C-ABI call (on the launching stream).
         Returns [(entry point, milliseconds)], used by bench.py for the per-kernel roofline."""
-        s = _lib.stream_ptr()
         evs = []
-        for fn, args, name in self.calls:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = fn(*args, s)
-            e1.record()
-            if rc != 0:
-                _lib.check(rc, name)
-            evs.append((name, args, e0, e1))
+        with _lib.on_device(self.device) as s:
+            for fn, args, name in self.calls:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args, s)
+                e1.record()
+                if rc != 0:
+                    _lib.check(rc, name)
+                evs.append((name, args, e0, e1))
         torch.cuda.synchronize(self.device)
         return [(name, args, e0.elapsed_time(e1)) for name, args, e0, e1 in evs]
 
@@ -206,15 +220,17 @@ class FramePlan:
     def capture(self):
         """Freeze the launch list into a CUDA graph (after one eager warm-up so that lazy
         cudaFuncSetAttribute calls are done)."""
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            self.launch()
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.launch()
-        self.graph = g
+        with _lib.on_device(self.device):
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.launch()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.launch()
+            self.graph = g
+            self.graph_pdl = bool(_lib.lib().deft_get_pdl())     # the PDL mode the launches were captured under
         return self
 
     @property

@@ -38,19 +38,30 @@ def _without_dataparallel_prefix(tensors):
     return out
 
 
-def _reconcile(loaded, own):
+def _reconcile(loaded, own, reset_hm=False, reuse_hm=False):
     """What load_state_dict(strict=False) should see: every key of the model, taken from the checkpoint when it is
-    there with the right shape, otherwise the model's current tensor.  Returns (merged, report lines)."""
+    there with the right shape, otherwise the model's current tensor.  Returns (merged, report lines).
+    reset_hm / reuse_hm (model.py:58-77): with reset_hm, `hm*` tensors whose leading dimension is 80 (COCO) or 1
+    (CrowdHuman) are treated like a shape mismatch even when the shapes agree; a mismatched tensor is then either
+    skipped or, with reuse_hm, its leading slice is reused (the reference's `a < a` comparison at model.py:70 is
+    always False, so the executed branch is `loaded[:required]`, which is what is restated here)."""
     merged, report = {}, []
     for key, value in loaded.items():
         if key not in own:
             report.append(f"Drop parameter {key}.")
             merged[key] = value                  # harmless under strict=False; kept so the behaviour matches
-        elif tuple(value.shape) != tuple(own[key].shape):
+            continue
+        mismatch = tuple(value.shape) != tuple(own[key].shape)
+        if not mismatch and reset_hm and key.startswith("hm") and value.dim() > 0 and value.shape[0] in (80, 1):
+            mismatch = True
+        if not mismatch:
+            merged[key] = value
+        elif reuse_hm:
+            report.append(f"Reusing parameter {key}, required shape{own[key].shape}, loaded shape{value.shape}.")
+            merged[key] = value[: own[key].shape[0]]
+        else:
             report.append(f"Skip loading parameter {key}, required shape{own[key].shape}, loaded shape{value.shape}.")
             merged[key] = own[key]
-        else:
-            merged[key] = value
     for key in own:
         if key not in loaded:
             report.append(f"No param {key}.")
@@ -70,7 +81,8 @@ def load_model(model, model_path, opt, optimizer=None):
     ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
     print("loaded {}, epoch {}".format(model_path, ckpt.get("epoch", "?") if isinstance(ckpt, dict) else "?"))
     tensors = ckpt["state_dict"] if isinstance(ckpt, dict) and "state_dict" in ckpt else ckpt
-    merged, report = _reconcile(_without_dataparallel_prefix(tensors), model.state_dict())
+    merged, report = _reconcile(_without_dataparallel_prefix(tensors), model.state_dict(), reset_hm=bool(getattr(opt, "reset_hm", False)),
+                                reuse_hm=bool(getattr(opt, "reuse_hm", False)))
     for line in report:
         print(line)
     model.load_state_dict(merged, strict=False)

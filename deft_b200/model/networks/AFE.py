@@ -9,8 +9,8 @@ Same constructor (``AFE_module(opt)``), same state_dict keys (``selector.{0..12}
 plus the B200 batched form ``affinity_batched`` (all memory frames in one call, result stays on device).
 The selector conv is evaluated only at the 4 bilinear corners of every centre (deft_afe_extract);
 the MLP runs as chained GEMMs over the live n x m pairs with the first layer decomposed
-(deft_afe_affinity).  Training-only pieces (forward/loss, AFE.py:74-86,235-328) are not on the
-inference hot path and are not implemented here.
+(deft_afe_affinity).  The training-side surface (forward/loss, AFE.py:74-86,235-328) is implemented as forward
+values in eval mode (deft_afe_forward_scores / deft_afe_loss); gradients and train-mode BN are row f4.
 """
 import numpy as np
 import torch
@@ -109,5 +109,53 @@ class AFE_module(nn.Module):
         f2 = self.forward_feature_extracter(image2, detection2)
         return self.forward_stacker_features(f1, f2, False)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("AFE_module.forward/loss are training-only (AFE.py:74-86,235-328); out of the inference hot path")
+    # -- a9 (training-side surface, forward pass only) ------------------------------------------
+    def _extract_batched(self, sources, centres):
+        """forward_selector_stacker1 (AFE.py:162-188) for a batch: sources = 13 maps [B,C,H,W], centres [B,N,1,1,2]
+        (padding rows hold 1.5 -> border sample, image.py:356-359) -> [B,N,Cemb]."""
+        pk = self.packed()
+        maps = [m if isinstance(m, ops.NHWC) else ops.as_nhwc(m) for m in sources]
+        B = maps[0].N
+        N = centres.shape[1]
+        out = torch.empty((B, N, sum(pk["sel_co"])), dtype=torch.float32, device=centres.device)
+        ws = None
+        for b in range(B):
+            mb = [ops.NHWC(m.t[b:b + 1], m.C) for m in maps]
+            ops.afe_extract(mb, pk["sel_w"], pk["sel_b"], pk["sel_co"], centres[b].reshape(-1, 2).float().contiguous(), self.align_corners,
+                            out=out[b], ws=ws)
+        return out
+
+    def forward(self, sources_pre, sources_next, l_pre, l_next):
+        """AFE.py:74-86: embeddings of both frames -> pairwise MLP over all P x P pairs -> [B,1,P+1,P+1] with the
+        false-object column/row appended (add_unmatched_dim).  Eval-mode BN (running statistics): the train-mode
+        batch statistics of ModleWithLoss (trainer.py:155-170) belong to the training engine."""
+        _lib.require_device(l_pre)
+        if self.training:
+            raise NotImplementedError("AFE_module.forward: eval-mode BN only (call .eval()); train-mode batch statistics are row f4")
+        P = self.max_object
+        if l_pre.shape[1] != P or l_next.shape[1] != P:
+            raise ValueError("AFE_module.forward: both centre tensors must hold max_object rows (generic_dataset pads them)")
+        x_pre = self._extract_batched(sources_pre, l_pre)
+        x_next = self._extract_batched(sources_next, l_next)
+        B, _, Cemb = x_pre.shape
+        pk = self.packed()["mlp"]
+        au, _ = ops.afe_project(x_pre.view(B * P, Cemb), pk, want_bv=False, flags=self._flags, tcF=B, tcP=P)
+        _, bv = ops.afe_project(x_next.view(B * P, Cemb), pk, want_au=False, flags=self._flags, tcF=B, tcP=P)
+        return ops.afe_forward_scores(au.view(B, P, 512), bv.view(B, P, 512), pk, self.false_constant, flags=self._flags)
+
+    def add_unmatched_dim(self, x):
+        """AFE.py:215-233 on a device tensor [B,1,P,P] (plumbing; forward() already returns the extended matrix)."""
+        ones_c = x.new_full(x.shape[:3] + (1,), self.false_constant)
+        x = torch.cat([x, ones_c], 3)
+        return torch.cat([x, x.new_full(x.shape[:2] + (1, x.shape[3]), self.false_constant)], 2)
+
+    def loss(self, input, target, mask0, mask1):
+        """AFE.py:235-328 (forward value): returns the reference's 8-tuple (loss_pre, loss_next, loss_similarity,
+        mean loss, accuracy_pre, accuracy_next, mean accuracy, indexes_pre [B,1,P])."""
+        _lib.require_device(input)
+        if input.shape[-1] != self.max_object + 1:
+            raise ValueError("AFE_module.loss: input must be [B,1,max_object+1,max_object+1]")
+        dev = input.device
+        u8 = lambda t: (t.to(dev) != 0).to(torch.uint8).contiguous()
+        out7, idx = ops.afe_loss(input.float().contiguous(), target.to(dev).float().contiguous(), u8(mask0), u8(mask1))
+        return (out7[0], out7[1], out7[2], out7[3], out7[4], out7[5], out7[6], idx)

@@ -192,16 +192,25 @@ class DLASeg(nn.Module):
 
     def plan_for(self, x, slot=0):
         """The frame plan (arena + launch list) for this input shape; `slot` > 0 asks for an additional, independent
-        arena (FramePipeline keeps two so that frame t+1's backbone can overlap frame t's decode/embedding tail)."""
-        key = (tuple(x.shape), x.device.index, self._flags(), slot)
+        arena (FramePipeline keeps several so that frame t+1's backbone can overlap frame t's decode/embedding tail)."""
+        return self.plan_for_shape(x.shape[0], x.shape[2], x.shape[3], x.device, slot)
+
+    def plan_for_shape(self, N, H, W, device, slot=0, u8_norm=None):
+        """u8_norm = (mean, std): a plan whose input slot is a uint8 HWC frame with the normalisation fused into the
+        stem (row f2)."""
+        # the PDL mode is part of the key: a captured graph bakes the launch attribute in (pipeline.py switches PDL off
+        # when several frames are in flight)
+        un = None if u8_norm is None else (tuple(float(v) for v in u8_norm[0]), tuple(float(v) for v in u8_norm[1]))
+        key = ((N, 3, H, W), device.index, self._flags(), slot, int(_lib.lib().deft_get_pdl()), un)
         p = self._plans.get(key)
         if p is None:
             if self.training:
                 raise _lib.DeftError("deft_b200.DLASeg runs eval-mode BN only: call .eval() (training is out of the hot path)")
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith("AFE.")}
-            p = FramePlan(sd, self.heads, x.shape[0], x.shape[2], x.shape[3], x.device, self._flags())
-            if self.use_cuda_graph:
-                p.capture()
+            with _lib.on_device(device):
+                p = FramePlan(sd, self.heads, N, H, W, device, self._flags(), u8_norm=un)
+                if self.use_cuda_graph:
+                    p.capture()
             self._plans[key] = p
         return p
 

@@ -15,6 +15,35 @@ from ._lib import check, int_array, lib, ptr_array, stream_ptr
 FLAG_RELU, FLAG_TENSORCORE, FLAG_TF32X1 = _lib.FLAG_RELU, _lib.FLAG_TENSORCORE, _lib.FLAG_TF32X1
 
 
+def _device_of(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            return a.device
+        if isinstance(a, NHWC):
+            return a.t.device
+        if isinstance(a, (list, tuple)) and a:
+            d = _device_of(a)
+            if d is not None:
+                return d
+    return None
+
+
+def _on_input_device(fn):
+    """Run the wrapped C-ABI call with the device of its first tensor argument current, so that the stream handed to
+    the library (stream_ptr()), the kernels' per-device attributes and the TMA descriptors all belong to the device
+    that owns the pointers -- a model on cuda:1 works while cuda:0 is current, like a torch nn.Module does."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        d = _device_of(args) or _device_of(tuple(kw.values()))
+        if d is None or d.type != "cuda" or d.index is None or d.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with _lib.on_device(d):
+            return fn(*args, **kw)
+    return wrapper
+
+
 class NHWC:
     """A channels-last activation: memory [N,H,W,pitch] fp32, logical channels C <= pitch."""
     __slots__ = ("t", "N", "H", "W", "C", "pitch", "ptr")
@@ -35,6 +64,7 @@ class NHWC:
         return self.t[..., : self.C].permute(0, 3, 1, 2)
 
 
+@_on_input_device
 def as_nhwc(x):
     """Accept a [N,C,H,W] tensor in either memory format; returns an NHWC handle (zero-copy when the
     tensor already is channels-last, otherwise one deft_nchw_to_nhwc launch)."""
@@ -53,6 +83,7 @@ def as_nhwc(x):
     return out
 
 
+@_on_input_device
 def to_nchw(a: NHWC):
     out = torch.empty((a.N, a.C, a.H, a.W), dtype=torch.float32, device=a.t.device)
     check(lib().deft_nhwc_to_nchw(a.ptr, a.pitch, out.data_ptr(), a.N, a.C, a.H, a.W, stream_ptr()), "nhwc_to_nchw")
@@ -66,6 +97,7 @@ def _p(t):
 KIND_CONV, KIND_DCN, KIND_HEADS = 0, 1, 2
 
 
+@_on_input_device
 def tc_pack(wp, ldw, K, M, kind=KIND_CONV, taps=1):
     """Packed weight Wp[K][ldw] -> (tcgen05 tile-image blob, tile N) for an M-row problem; one kernel launch,
     done at load time.  `taps` = KH*KW of the conv that will consume it (its K order is channel-block-major when
@@ -82,6 +114,7 @@ def tc_scratch(ldw, K, M, kind, device):
     return torch.empty(n, dtype=torch.uint8, device=device) if n else None
 
 
+@_on_input_device
 def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, residual=None, out=None, flags=0, w_tc=None, tc_bn=0,
                   ws=None):
     s0 = srcs[0]
@@ -103,6 +136,7 @@ def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, 
     return out
 
 
+@_on_input_device
 def stem_conv7x7(x_nchw, wp, scale, shift, out=None):
     N, _, H, W = x_nchw.shape
     if out is None:
@@ -112,6 +146,7 @@ def stem_conv7x7(x_nchw, wp, scale, shift, out=None):
     return out
 
 
+@_on_input_device
 def maxpool2x2(a: NHWC, out=None):
     if out is None:
         out = NHWC.empty(a.N, a.H // 2, a.W // 2, a.C, a.t.device)
@@ -124,6 +159,7 @@ def dcn_workspace(N, H, W, cin, cout, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
+@_on_input_device
 def dcnv2_forward(a: NHWC, pk, relu, ws=None, out=None, flags=0):
     if ws is None:
         ws = dcn_workspace(a.N, a.H, a.W, pk["cin"], pk["cout"], a.t.device)
@@ -148,6 +184,7 @@ def dcn_tc_blobs(pk, M):
     return cache[M]
 
 
+@_on_input_device
 def upsample_add(a: NHWC, wp, f, skip=None, out=None):
     if out is None:
         out = NHWC.empty(a.N, a.H * f, a.W * f, a.C, a.t.device)
@@ -157,6 +194,7 @@ def upsample_add(a: NHWC, wp, f, skip=None, out=None):
     return out
 
 
+@_on_input_device
 def heads_forward(feat: NHWC, hp, outs=None, ws=None, flags=0):
     nh = len(hp["head_c"])
     if ws is None:
@@ -173,11 +211,13 @@ def heads_forward(feat: NHWC, hp, outs=None, ws=None, flags=0):
     return outs
 
 
+@_on_input_device
 def sigmoid_output_(hm, dep=None, depth_scale=1.0):
     check(lib().deft_sigmoid_output(_p(hm), 0 if hm is None else hm.numel(), _p(dep), 0 if dep is None else dep.numel(),
                                     float(depth_scale), stream_ptr()), "sigmoid_output")
 
 
+@_on_input_device
 def decode(hm, K, reg=None, wh=None, ltrb_amodal=None, ws=None):
     _lib.require_device(hm)
     hm = hm.contiguous()
@@ -200,6 +240,7 @@ def decode(hm, K, reg=None, wh=None, ltrb_amodal=None, ws=None):
     return dict(scores=scores, inds=inds, clses=clses, ys=ys, xs=xs, bboxes=bboxes, bboxes_amodal=bba)
 
 
+@_on_input_device
 def gather_feat(feat, inds):
     feat = feat.contiguous()
     B, Cc, H, W = feat.shape
@@ -209,6 +250,7 @@ def gather_feat(feat, inds):
     return out
 
 
+@_on_input_device
 def boxes_to_centres(boxes, W, H, out=None):
     """boxes [N,4] device (x1,y1,x2,y2) in a WxH frame -> [N,2] centres in [-1,1] (image.py:391-412)."""
     N = boxes.shape[0]
@@ -218,6 +260,7 @@ def boxes_to_centres(boxes, W, H, out=None):
     return out
 
 
+@_on_input_device
 def afe_extract(maps, sel_w, sel_b, sel_co, centres, align_corners=False, out=None, ws=None):
     """maps: 13 NHWC handles (batch 1); centres [N,2] device tensor -> emb [N, Cemb]."""
     N = centres.shape[0]
@@ -234,6 +277,7 @@ def afe_extract(maps, sel_w, sel_b, sel_co, centres, align_corners=False, out=No
     return out
 
 
+@_on_input_device
 def afe_affinity(xp, counts, xn, m, P, pk, out=None, ws=None, flags=0):
     """xp [F,P,Cemb] device slab, counts: list[int] (len F), xn [>=m, Cemb]; -> out [F,P,P+1]."""
     F = xp.shape[0]
@@ -243,15 +287,7 @@ def afe_affinity(xp, counts, xn, m, P, pk, out=None, ws=None, flags=0):
         ws = torch.empty(lib().deft_afe_affinity_workspace_bytes(F, P, cemb), dtype=torch.uint8, device=dev)
     if out is None:
         out = torch.zeros((F, P, P + 1), dtype=torch.float32, device=dev)
-    tc, tcbn = None, None
-    if flags & FLAG_TENSORCORE:
-        cache = pk.setdefault("_tc", {})
-        if (F, P) not in cache:       # any valid tile works for any M; pick tiles for the nominal (full) problem sizes
-            nominal = {"w1a": F * P, "w1b": P, "w2": F * P * P, "w3": F * P * P, "w4": F * P * P}
-            cache[(F, P)] = [tc_pack(pk[k], pk[k].shape[1], pk[k].shape[0], nominal[k]) for k in ("w1a", "w1b", "w2", "w3", "w4")]
-        blobs = cache[(F, P)]
-        tc = ptr_array([b.data_ptr() for b, _ in blobs])
-        tcbn = int_array([bn for _, bn in blobs])
+    tc, tcbn = _affinity_tc(pk, F, P, flags)
     check(lib().deft_afe_affinity(xp.data_ptr(), int_array(list(counts)), F, xn.data_ptr(), m, P, cemb, pk["w1a"].data_ptr(),
                                   pk["w1b"].data_ptr(), pk["sh1"].data_ptr(), pk["w2"].data_ptr(), pk["sc2"].data_ptr(),
                                   pk["sh2"].data_ptr(), pk["w3"].data_ptr(), pk["sc3"].data_ptr(), pk["sh3"].data_ptr(),
@@ -260,6 +296,7 @@ def afe_affinity(xp, counts, xn, m, P, pk, out=None, ws=None, flags=0):
     return out
 
 
+@_on_input_device
 def lstm_step(x, h, c, w, nout, h_out=None, c_out=None, pred=None):
     T, F = x.shape
     dev = x.device
@@ -271,3 +308,133 @@ def lstm_step(x, h, c, w, nout, h_out=None, c_out=None, pred=None):
                                w["w2"].data_ptr(), w["b2"].data_ptr(), T, F, nout, h_out.data_ptr(), c_out.data_ptr(),
                                pred.data_ptr(), stream_ptr()), "lstm_step")
     return h_out, c_out, pred
+
+
+# ---------------------------------------------------------------------------------------------- a8 cached / a9 / f1 / f2
+def _affinity_tc(pk, F, P, flags):
+    """tcgen05 tile images of the five MLP weights (cached in the pack dict) as ctypes arrays, or (None, None)."""
+    if not (flags & FLAG_TENSORCORE):
+        return None, None
+    cache = pk.setdefault("_tc", {})
+    if (F, P) not in cache:       # any valid tile works for any M; pick tiles for the nominal (full) problem sizes
+        nominal = {"w1a": F * P, "w1b": P, "w2": F * P * P, "w3": F * P * P, "w4": F * P * P}
+        cache[(F, P)] = [tc_pack(pk[k], pk[k].shape[1], pk[k].shape[0], nominal[k]) for k in ("w1a", "w1b", "w2", "w3", "w4")]
+    blobs = cache[(F, P)]
+    return ptr_array([b.data_ptr() for b, _ in blobs]), int_array([bn for _, bn in blobs])
+
+
+def _mlp_args(pk):
+    return (pk["w2"].data_ptr(), pk["sc2"].data_ptr(), pk["sh2"].data_ptr(), pk["w3"].data_ptr(), pk["sc3"].data_ptr(), pk["sh3"].data_ptr(),
+            pk["w4"].data_ptr(), pk["b4"].data_ptr(), pk["w5"].data_ptr(), C.c_float(pk["b5"]))
+
+
+@_on_input_device
+def afe_project(emb, pk, au=None, bv=None, want_au=True, want_bv=True, flags=0, tcF=1, tcP=None):
+    """emb [rows, Cemb] -> (Au' [rows,512] with the folded bias/BN shift, Bv' [rows,512]) of the decomposed first MLP layer."""
+    rows = emb.shape[0]
+    dev = emb.device
+    if want_au and au is None:
+        au = torch.empty((rows, 512), dtype=torch.float32, device=dev)
+    if want_bv and bv is None:
+        bv = torch.empty((rows, 512), dtype=torch.float32, device=dev)
+    tc, tcbn = _affinity_tc(pk, tcF, tcP or rows, flags)
+    check(lib().deft_afe_project(emb.data_ptr(), rows, pk["cemb"], pk["w1a"].data_ptr(), pk["w1b"].data_ptr(), pk["sh1"].data_ptr(), tc, tcbn,
+                                 _p(au) if want_au else None, _p(bv) if want_bv else None, flags, stream_ptr()), "afe_project")
+    return au, bv
+
+
+@_on_input_device
+def afe_affinity_cached(au_mem, n_dev, bv, m_max, P, pk, rows=None, m_dev=None, out=None, ws=None, flags=0):
+    """au_mem [F,P,512] cached Au' of the memory ring, n_dev int32[F] live rows (device), bv [>=m_max,512] -> out [F,P,P+1]."""
+    F = au_mem.shape[0]
+    rows = P if rows is None else rows
+    dev = au_mem.device
+    need = lib().deft_afe_pairs_workspace_bytes(F, rows, m_max)
+    if ws is None:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((F, P, P + 1), dtype=torch.float32, device=dev)
+    tc, tcbn = _affinity_tc(pk, F, P, flags)
+    check(lib().deft_afe_affinity_cached(au_mem.data_ptr(), F, P, rows, n_dev.data_ptr(), bv.data_ptr(), m_max, _p(m_dev), *_mlp_args(pk), tc, tcbn,
+                                         out.data_ptr(), flags, ws.data_ptr(), ws.numel(), stream_ptr()), "afe_affinity_cached")
+    return out
+
+
+@_on_input_device
+def afe_forward_scores(au, bv, pk, false_constant=1.0, out=None, ws=None, flags=0):
+    """au, bv [B,P,512] -> [B,1,P+1,P+1] (AFE.forward after the extractor + add_unmatched_dim)."""
+    B, P, _ = au.shape
+    dev = au.device
+    if ws is None:
+        ws = torch.empty(lib().deft_afe_pairs_workspace_bytes(B, P, P), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((B, 1, P + 1, P + 1), dtype=torch.float32, device=dev)
+    tc, tcbn = _affinity_tc(pk, B, P, flags)
+    check(lib().deft_afe_forward_scores(au.data_ptr(), bv.data_ptr(), B, P, *_mlp_args(pk), tc, tcbn, C.c_float(false_constant), out.data_ptr(), flags,
+                                        ws.data_ptr(), ws.numel(), stream_ptr()), "afe_forward_scores")
+    return out
+
+
+@_on_input_device
+def afe_loss(inp, target, mask0, mask1):
+    """AFE_module.loss forward; returns (out7 float32[7] device, indexes_pre int64 [B,1,P] device)."""
+    B, _, Q, _ = inp.shape
+    P = Q - 1
+    dev = inp.device
+    out7 = torch.empty(7, dtype=torch.float32, device=dev)
+    idx = torch.empty((B, 1, P), dtype=torch.int64, device=dev)
+    ws = torch.empty(lib().deft_afe_loss_workspace_bytes(B, P), dtype=torch.uint8, device=dev)
+    check(lib().deft_afe_loss(inp.data_ptr(), target.data_ptr(), mask0.data_ptr(), mask1.data_ptr(), B, P, out7.data_ptr(), idx.data_ptr(),
+                              ws.data_ptr(), ws.numel(), stream_ptr()), "afe_loss")
+    return out7, idx
+
+
+@_on_input_device
+def memory_push(emb, au, rows, C_, F, P, clock, slot_frame, counts, memory, au_mem, m_dev=None):
+    check(lib().deft_memory_push(emb.data_ptr(), _p(au), rows, _p(m_dev), C_, F, P, clock.data_ptr(), slot_frame.data_ptr(), counts.data_ptr(),
+                                 memory.data_ptr(), _p(au_mem), stream_ptr()), "memory_push")
+
+
+@_on_input_device
+def track_similarity(aff, clock, slot_frame, counts, node_frame, node_id, node_cnt, m, mm, m_frame, sim, cost=None, m_dev=None, max_track_node=50,
+                     decay=1.0, decay2=0.01):
+    F, P, _ = aff.shape
+    T = node_cnt.shape[0]
+    check(lib().deft_track_similarity(aff.data_ptr(), F, P, clock.data_ptr(), slot_frame.data_ptr(), counts.data_ptr(), node_frame.data_ptr(),
+                                      node_id.data_ptr(), node_cnt.data_ptr(), T, m, _p(m_dev), mm, m_frame, max_track_node, C.c_double(decay),
+                                      C.c_double(decay2), sim.data_ptr(), _p(cost), stream_ptr()), "track_similarity")
+    return sim, cost
+
+
+@_on_input_device
+def track_append(match, clock, node_frame, node_id, node_cnt):
+    check(lib().deft_track_append(match.data_ptr(), clock.data_ptr(), node_cnt.shape[0], node_frame.data_ptr(), node_id.data_ptr(),
+                                  node_cnt.data_ptr(), stream_ptr()), "track_append")
+
+
+@_on_input_device
+def count_above(scores, thresh, out):
+    check(lib().deft_count_above(scores.data_ptr(), scores.numel(), C.c_float(thresh), out.data_ptr(), stream_ptr()), "count_above")
+    return out
+
+
+@_on_input_device
+def stem_conv7x7_u8(img_u8, mean, std, wp, scale, shift, out=None, x_nchw=None):
+    """img_u8 [N,H,W,3] uint8 (device) -> stem output NHWC [N,H,W,16]; normalisation fused (detector.py:408-409)."""
+    N, H, W, _ = img_u8.shape
+    if out is None:
+        out = NHWC.empty(N, H, W, 16, img_u8.device)
+    check(lib().deft_stem_conv7x7_u8(img_u8.data_ptr(), N, H, W, _lib.float_array(mean), _lib.float_array(std), wp.data_ptr(), scale.data_ptr(),
+                                     shift.data_ptr(), out.ptr, out.pitch, _p(x_nchw), stream_ptr()), "stem_conv7x7_u8")
+    return out
+
+
+@_on_input_device
+def preprocess_warp(img_u8, inv_affine, mean, std, H, W, out=None):
+    """img_u8 [h,w,3] uint8 device; inv_affine: 6 floats mapping network-input (x,y) -> source (x,y) -> fp32 [1,3,H,W]."""
+    sh, sw, _ = img_u8.shape
+    if out is None:
+        out = torch.empty((1, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    check(lib().deft_preprocess_warp(img_u8.data_ptr(), sh, sw, _lib.float_array(inv_affine), _lib.float_array(mean), _lib.float_array(std),
+                                     out.data_ptr(), H, W, stream_ptr()), "preprocess_warp")
+    return out

@@ -56,10 +56,19 @@ unsigned long long deft_launch_count(void);
  * switches it off for depth > 1.  Applies to launches (and graph captures) made after the call. */
 void deft_set_pdl(int enabled);
 int deft_get_pdl(void);
+/* Engine observability.  Every GEMM-shaped entry point tries the tcgen05 engine first (DEFT_FLAG_TENSORCORE) and drops
+ * to the fp32 SIMT engine when the tensor-core dispatcher does not cover the shape.  deft_simt_fallback_count() counts
+ * those drops (a DLA-34 frame must report 0: tests/test_gpu_frame.py), deft_debug_set_engine_log(1) or
+ * DEFT_DEBUG_ENGINE=1 prints one stderr line per drop.  deft_debug_set_trace: bring-up only -- a device buffer of
+ * 4*96*4 int64 into which CTA 0 of the tcgen05 kernels stamps clock64() per protocol point (tools/tc_trace.py);
+ * NULL disarms it. */
+unsigned long long deft_simt_fallback_count(void);
+void deft_debug_set_engine_log(int enabled);
+void deft_debug_set_trace(void* device_buffer);
 
 /* ---- tcgen05 weight images: a packed weight Wp[K][ldw] re-laid as ready-to-copy shared-memory tiles
  * ([n_tile][k_block][hi|lo][bn x 32] fp32, SWIZZLE_128B, split x = hi + lo for 3xTF32).
- * kind: 0 = conv / plain GEMM, 1 = deformable gather (bn <= 64), 2 = fused heads (bn = 256).
+ * kind: 0 = conv / plain GEMM, 1 = deformable gather (bn <= 128), 2 = fused heads (bn = 256).
  * deft_tc_tile_n picks bn for an M-row problem; the same bn must be passed to every call that uses the blob.
  * deft_tc_scratch_bytes: split-K scratch the engine wants for that problem (0 = none; optional, without it
  * small-M layers simply run unsplit). */
@@ -161,7 +170,7 @@ int deft_afe_extract(const float* const* maps_host, const int* pitch_host, const
  *   w1a,w1b [Cemb][512] + sh1a[512] (all of bias/BN shift), w2 [512][256]+sc2,sh2, w3 [256][128]+sc3,sh3,
  *   w4 [128][64]+b4, w5[64], b5.
  * out [F,P,P+1]: out[f,i,j<m] = max(softmax_row, softmax_col)[i,j]; out[f,i,m] = softmax_row[i,P];
- * rows >= n_f / cols > m untouched.  P = max_object (the softmax denominators contain the
+ * the rest of each [P, P+1] block is written as 0 (a reused buffer never shows an earlier frame).  P = max_object (the softmax denominators contain the
  * (P-n)/(P-m) zero entries and the constant-1 row/col exactly as the reference). */
 size_t deft_afe_affinity_workspace_bytes(int F, int P, int Cemb);
 int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn, int m, int P, int Cemb,
@@ -171,6 +180,69 @@ int deft_afe_affinity(const float* xp, const int* n_host, int F, const float* xn
                       const float* w4, const float* b4, const float* w5, float b5,
                       const float* const* tc_host /* {w1a,w1b,w2,w3,w4} tile images or NULL */, const int* tc_bn_host,
                       float* out, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
+
+/* ---- a8, device-resident form: the first MLP layer is linear in the concatenated pair, so
+ * Au' = bnfold(W1a bn(u) + b1) of a MEMORY frame never changes while the frame sits in the recorder's ring
+ * (tracker.py:59-90).  deft_afe_project computes Au' and/or Bv' for `rows` embeddings ([rows,512] each, NULL = skip);
+ * deft_afe_affinity_cached runs layers 2..5 + the dual softmax against a ring au_mem [F,P,512] whose live row counts
+ * n_dev[F] (and optionally the live detection count *m_dev) stay on the device: the pair grid is the fixed
+ * F x rows x m_max block (dead rows / columns are computed and ignored by the softmax), so the call is
+ * graph-capturable with no host knowledge of the counts.  ws >= deft_afe_pairs_workspace_bytes(F, rows, m_max). */
+size_t deft_afe_pairs_workspace_bytes(int F, int rows, int cols);
+int deft_afe_project(const float* emb, int rows, int Cemb, const float* w1a, const float* w1b, const float* sh1,
+                     const float* const* tc_host, const int* tc_bn_host, float* au, float* bv, unsigned flags, deft_stream_t s);
+int deft_afe_affinity_cached(const float* au_mem, int F, int P, int rows, const int* n_dev, const float* bv, int m_max,
+                             const int* m_dev, const float* w2, const float* sc2, const float* sh2, const float* w3,
+                             const float* sc3, const float* sh3, const float* w4, const float* b4, const float* w5, float b5,
+                             const float* const* tc_host, const int* tc_bn_host, float* out, unsigned flags, void* ws,
+                             size_t ws_bytes, deft_stream_t s);
+
+/* ---- a9: AFE_module.forward (AFE.py:74-86) after the extractor, eval-mode BN: au/bv [B,P,512] = projected embeddings
+ * of the previous / next frame of every batch element (padding rows included, as the reference keeps them) ->
+ * out [B,1,P+1,P+1] = relu-MLP scores with the false-object column and row of `false_constant` appended
+ * (add_unmatched_dim, AFE.py:215-233).  ws >= deft_afe_pairs_workspace_bytes(B, P, P). */
+int deft_afe_forward_scores(const float* au, const float* bv, int B, int P, const float* w2, const float* sc2, const float* sh2,
+                            const float* w3, const float* sc3, const float* sh3, const float* w4, const float* b4,
+                            const float* w5, float b5, const float* const* tc_host, const int* tc_bn_host, float false_constant,
+                            float* out, unsigned flags, void* ws, size_t ws_bytes, deft_stream_t s);
+/* AFE_module.loss forward (AFE.py:235-328): input/target [B,1,P+1,P+1] fp32, mask0/mask1 [B,1,P+1] uint8 ->
+ * out7 = {loss_pre, loss_next, loss_similarity, (loss_pre+loss_next+loss+loss_similarity)/4, accuracy_pre,
+ * accuracy_next, (accuracy_pre+accuracy_next)/2}, indexes_pre [B,1,P] int64 (first maximum wins, as torch.max). */
+size_t deft_afe_loss_workspace_bytes(int B, int P);
+int deft_afe_loss(const float* input, const float* target, const unsigned char* mask0, const unsigned char* mask1, int B, int P,
+                  float* out7, long long* indexes_pre, void* ws, size_t ws_bytes, deft_stream_t s);
+
+/* ---- f1: the recorder / track memory on the device (tracker.py:46-137, 219-252, 886-894).
+ * State, all caller-owned device memory: clock int[2] (clock[0] = index of the frame being associated),
+ * slot_frame int[F] (-1 = empty; frame t lives in slot t % F), counts int[F], memory [F,P,C], au_mem [F,P,512],
+ * node_frame/node_id int[T, L] (L = deft_track_nodes_per_track(), oldest first), node_cnt int[T].
+ *  deft_memory_push      FeatureRecorder.update's bookkeeping: rows (or *m_dev) embeddings (+ their Au') -> slot
+ *                        clock % F, slot_frame/counts updated, clock advanced.
+ *  deft_track_similarity STrack.get_similarity for all T tracks: rows of aff [F,P,P+1] named by the track's nodes,
+ *                        times the recorder's decay (decay^(d/3) for d < m_frame, else decay2^(d/3)), median over the
+ *                        last mm rows (all mm+1 when there are exactly mm+1) -> sim [T,P+1] (live [:, :m+1], tracks
+ *                        without a usable node: zeros) and cost [T,P] = 1 - sim[:, :m] (NULL = skip).
+ *  deft_track_append     after association: match[t] = detection of track t or -1 -> node (clock, det) appended.
+ *  deft_count_above      number of scores > thresh (merge_outputs' cut, detector.py:577-583) as a device count. */
+int deft_track_nodes_per_track(void);
+int deft_memory_push(const float* emb, const float* au, int rows, const int* m_dev, int C, int F, int P, int* clock,
+                     int* slot_frame, int* counts, float* memory, float* au_mem, deft_stream_t s);
+int deft_track_similarity(const float* aff, int F, int P, const int* clock, const int* slot_frame, const int* counts,
+                          const int* node_frame, const int* node_id, const int* node_cnt, int T, int m, const int* m_dev,
+                          int mm, int m_frame, int max_track_node, double decay, double decay2, float* sim, float* cost,
+                          deft_stream_t s);
+int deft_track_append(const int* match, const int* clock, int T, int* node_frame, int* node_id, int* node_cnt, deft_stream_t s);
+int deft_count_above(const float* scores, int K, float thresh, int* out, deft_stream_t s);
+
+/* ---- f2: pre-processing (detector.py:377-422).  deft_stem_conv7x7_u8 = deft_stem_conv7x7 reading a uint8 HWC frame
+ * [N,H,W,3] already at network resolution, normalisation (u8/255 - mean[c])/std[c] fused into the load (x_nchw: optional
+ * fp32 NCHW copy of the normalised frame, NULL = none).  deft_preprocess_warp: general inverse-affine bilinear warp +
+ * normalisation of a [src_h,src_w,3] uint8 frame into fp32 NCHW [3,H,W] (inv_affine: host float[6], dst -> src). */
+int deft_stem_conv7x7_u8(const unsigned char* img, int N, int H, int W, const float* mean_host, const float* std_host,
+                         const float* w_packed, const float* scale, const float* shift, float* out, int out_pitch,
+                         float* x_nchw, deft_stream_t s);
+int deft_preprocess_warp(const unsigned char* img, int src_h, int src_w, const float* inv_affine_host, const float* mean_host,
+                         const float* std_host, float* out_nchw, int H, int W, deft_stream_t s);
 
 /* ---- a10: KalmanFilterLSTM.predict (kalman_filter_lstm.py:65-78) for T independent tracks in one
  * launch: one LSTM step (gate order i,f,g,o) + out1 (128->64, no activation) + out2 (64->nout).

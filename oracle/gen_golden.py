@@ -131,6 +131,56 @@ def gen_lstm():
     print("lstm ok")
 
 
+def afe_train_inputs(B, P, dataset="mot", seed_tag="a9"):
+    """Seeded inputs of the training-side AFE surface: 13 FeatureMaps per frame pair (small maps, reference channel
+    list AFE.py:15), centre tensors with 1.5-padded rows (image.py:356-359), a one-to-one label matrix with
+    false-object assignments and the matching uint8 masks (generic_dataset.py builds them the same way)."""
+    chans = spec.SELECTOR_IN
+    sizes = [(24, 40), (12, 20), (6, 10), (3, 5), (2, 3), (1, 2), (6, 10), (3, 5), (2, 3), (1, 2), (6, 10), (6, 10), (6, 10)]
+    fm_pre = [spec.make_input((B, c, h, w), tag=f"{seed_tag}_pre{k}").abs() for k, (c, (h, w)) in enumerate(zip(chans, sizes))]
+    fm_next = [spec.make_input((B, c, h, w), tag=f"{seed_tag}_next{k}").abs() for k, (c, (h, w)) in enumerate(zip(chans, sizes))]
+    l_pre = spec.make_uniform((B, P, 1, 1, 2), -1, 1, tag=f"{seed_tag}_lpre")
+    l_next = spec.make_uniform((B, P, 1, 1, 2), -1, 1, tag=f"{seed_tag}_lnext")
+    g = torch.Generator(); g.manual_seed(4242)
+    target = torch.zeros(B, 1, P + 1, P + 1)
+    mask0 = torch.zeros(B, 1, P + 1, dtype=torch.uint8)
+    mask1 = torch.zeros(B, 1, P + 1, dtype=torch.uint8)
+    for b in range(B):
+        n_pre, n_next = P // 3 + 5 * b + 1, P // 2 - 3 * b
+        l_pre[b, n_pre:] = 1.5
+        l_next[b, n_next:] = 1.5
+        mask0[b, 0, :n_pre] = 1; mask0[b, 0, P] = 1
+        mask1[b, 0, :n_next] = 1; mask1[b, 0, P] = 1
+        perm = torch.randperm(n_next, generator=g)
+        for i in range(n_pre):                       # two thirds of the previous objects survive, the rest disappear
+            if i < len(perm) and i % 3 != 2:
+                target[b, 0, i, perm[i]] = 1
+            else:
+                target[b, 0, i, P] = 1
+        matched = target[b, 0, :n_pre, :n_next].sum(0)
+        for j in range(n_next):                      # unmatched next objects are new: row P
+            if matched[j] == 0:
+                target[b, 0, P, j] = 1
+    return fm_pre, fm_next, l_pre, l_next, target, mask0, mask1
+
+
+def gen_afe_train():
+    """REAL AFE_module.forward (AFE.py:74-86) and .loss (235-328), eval mode, B=2, P=100."""
+    _, AFE, _ = ref_loader.load()
+    B, P = 2, 100
+    opt = ref_loader.make_opt("mot", P)
+    mod = AFE.AFE_module(opt).eval()
+    sd_all = spec.make_state_dict(spec.dlaseg_spec(spec.MOT_HEADS))
+    mod.load_state_dict({k[4:]: v for k, v in sd_all.items() if k.startswith("AFE.")}, strict=True)
+    fm_pre, fm_next, l_pre, l_next, target, mask0, mask1 = afe_train_inputs(B, P)
+    with torch.no_grad():
+        x = mod(fm_pre, fm_next, l_pre, l_next)
+        res = mod.loss(x, target, mask0.bool(), mask1.bool())     # bool masks: torch 2.x no longer indexes with uint8
+    g = {"meta": dict(B=B, P=P), "x": x.clone(), "loss": [float(v) for v in res[:7]], "indexes_pre": res[7].clone()}
+    torch.save(g, os.path.join(OUT, "afe_train_forward.pt"))
+    print("afe train forward/loss ok:", g["loss"])
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference not present; goldens can only be generated in the build container")
@@ -142,6 +192,7 @@ def main():
     gen_dcn()
     gen_decode_plateau()
     gen_lstm()
+    gen_afe_train()
 
 
 if __name__ == "__main__":

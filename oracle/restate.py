@@ -305,3 +305,137 @@ def lstm_predict(sd, h0, c0, x, max_fut):
     y = hn @ sd["out1.weight"].t() + sd["out1.bias"]
     y = y @ sd["out2.weight"].t() + sd["out2.bias"]
     return hn, cn, y.view(x.shape[0], max_fut, -1)
+
+
+# --------------------------------------------------------------------------- a9: AFE.forward / add_unmatched_dim / loss
+def afe_forward(sd, fm_pre, fm_next, l_pre, l_next, max_object, false_constant=1.0):
+    """AFE_module.forward (AFE.py:74-86) in eval mode: forward_selector_stacker1 on both frames, forward_stacker2
+    (190-207: both sides through the SAME stacker2_bn), forward_final (209-213), add_unmatched_dim (215-233).
+    Nothing is zeroed: padded centres (1.5 -> border sample) take part like real ones.
+    fm_*: 13 maps [B,C,H,W]; l_*: [B,P,1,1,2] -> [B,1,P+1,P+1]."""
+    P = max_object
+    xp = afe_extract(sd, fm_pre, l_pre)                          # [B,P,C]
+    xn = afe_extract(sd, fm_next, l_next)
+    B = xp.shape[0]
+    bn = lambda p, x: (x - sd[p + ".running_mean"]) / torch.sqrt(sd[p + ".running_var"] + EPS) * sd[p + ".weight"] + sd[p + ".bias"]
+    out = torch.full((B, 1, P + 1, P + 1), float(false_constant))
+    for b in range(B):
+        u, v = bn("AFE.stacker2_bn", xp[b]), bn("AFE.stacker2_bn", xn[b])
+        z = torch.cat([u.unsqueeze(1).expand(P, P, -1), v.unsqueeze(0).expand(P, P, -1)], 2).reshape(P * P, -1)
+        for idx, has_bn in ((0, True), (3, True), (6, True), (9, False), (11, False)):
+            w = sd[f"AFE.final_net.{idx}.weight"]
+            z = z @ w.view(w.shape[0], -1).t() + sd[f"AFE.final_net.{idx}.bias"]
+            if has_bn:
+                z = bn(f"AFE.final_net.{idx + 1}", z)
+            z = F.relu(z)
+        out[b, 0, :P, :P] = z.view(P, P)
+    return out
+
+
+def afe_loss(inp, target, mask0, mask1, max_object):
+    """AFE_module.loss (AFE.py:235-328), forward values.  inp/target [B,1,Q,Q] (Q = P+1), mask0/mask1 [B,1,Q] (0/1).
+    Returns the reference's 8-tuple as Python floats + indexes_pre [B,1,P] int64."""
+    P = max_object
+    m0 = mask0.float().unsqueeze(3).repeat(1, 1, 1, P + 1)       # row mask      (AFE.py:238)
+    m1 = mask1.float().unsqueeze(2).repeat(1, 1, P + 1, 1)       # column mask   (AFE.py:239)
+    region = m0 * m1
+    region_pre = region.clone(); region_pre[:, :, P, :] = 0      # 249-250
+    region_next = region.clone(); region_next[:, :, :, P] = 0    # 251-252
+    region_union = region_pre * region_next
+    input_pre = F.softmax(region_pre * inp, dim=3)               # 255
+    input_next = F.softmax(region_next * inp, dim=2)             # 256
+    input_all = input_pre.clone()
+    input_all[:, :, :P, :P] = ((input_pre + input_next) / 2.0)[:, :, :P, :P]
+    target = target.float()
+    t_pre, t_next, t_union = region_pre * target, region_next * target, region_union * target
+    n_all, n_pre, n_next, n_union = target.sum(), t_pre.sum(), t_next.sum(), t_union.sum()
+    loss_pre = -(t_pre * torch.log(input_pre)).sum()
+    if int(n_pre.item()):
+        loss_pre = loss_pre / n_pre
+    loss_next = -(t_next * torch.log(input_next)).sum()
+    if int(n_next.item()):
+        loss_next = loss_next / n_next
+    loss = -(t_pre * torch.log(input_all)).sum()
+    if int(n_pre.item()) and int(n_next.item()):
+        loss = loss / n_pre
+    loss_sim = (t_union * torch.abs((1 - input_pre) - (1 - input_next))).sum()
+    if int(n_union.item()):
+        loss_sim = loss_sim / n_all
+    mp = mask0[:, :, :-1] != 0
+    idx_t = t_pre.max(3)[1][:, :, :-1]
+    idx_pre = input_all.max(3)[1][:, :, :-1]
+    npre = int(mp.sum().item())
+    acc_pre = (idx_pre[mp] == idx_t[mp]).float().sum() / npre if npre else (idx_pre[mp] == idx_t[mp]).float().sum() + 1
+    mn = mask1[:, :, :-1] != 0
+    idx_t2 = t_next.max(2)[1][:, :, :-1]
+    idx_next = input_next.max(2)[1][:, :, :-1]
+    nnext = int(mn.sum().item())
+    acc_next = (idx_next[mn] == idx_t2[mn]).float().sum() / nnext if nnext else (idx_next[mn] == idx_t2[mn]).float().sum() + 1
+    vals = [loss_pre, loss_next, loss_sim, (loss_pre + loss_next + loss + loss_sim) / 4.0, acc_pre, acc_next, (acc_pre + acc_next) / 2.0]
+    return [float(v) for v in vals], idx_pre
+
+
+# --------------------------------------------------------------------------- f1: recorder decay + per-track median
+def recorder_similarity(aff_by_frame, frame_index, dataset="mot", decay=1.0, decay2=0.01):
+    """FeatureRecorder.update's loop (utils/tracker.py:76-90; constants 22-25): aff_by_frame {pre_index: np[n_pre, m+1]}
+    (forward_stacker_features(..., fill_up_column=False)) -> {pre_index: similarity * delta}, float32 like the reference
+    (numpy float32 array times a Python float)."""
+    m_frame = 5 if dataset == "kitti_tracking" else (3 if dataset == "nuscenes" else 10)
+    out = {}
+    for pre_index, sim in aff_by_frame.items():
+        d = frame_index - pre_index
+        delta = pow(decay, d / 3.0) if d < m_frame else pow(decay2, d / 3.0)
+        out[pre_index] = (np.asarray(sim, dtype=np.float32) * delta).astype(np.float32)
+    return out
+
+
+def track_similarity(nodes, frame_index, all_similarity, dataset="mot", max_track_node=50):
+    """STrack.get_similarity (utils/tracker.py:219-252).  nodes: [(frame_index, det_id)] oldest first;
+    all_similarity: {pre_index: np[n_pre, m+1]} of the current frame (recorder_similarity's output).
+    Returns np.float32 [m+1] or None (no usable node)."""
+    rows = []
+    for f, i in nodes:
+        if frame_index - f >= max_track_node:
+            continue
+        rows.append(all_similarity[f][i, :])
+    if not rows:
+        return None
+    a = np.array(rows)
+    mm = 2 if dataset == "nuscenes" else 4
+    if a.shape[0] > mm:
+        if a.shape[0] <= mm + 1:
+            a1, a2 = a[:, : a.shape[1] - 1], np.median(a[:, -1:], axis=0)
+        else:
+            a1, a2 = a[a.shape[0] - mm:, : a.shape[1] - 1], np.median(a[a.shape[0] - mm:, -1:], axis=0)
+        return np.concatenate((np.median(a1, axis=0), a2), axis=0)
+    return np.median(a, axis=0)
+
+
+# --------------------------------------------------------------------------- f2: pre-processing
+def normalize_u8(img_u8_hwc, mean, std):
+    """Detector.pre_process (detector.py:408-410): ((img / 255. - mean) / std).astype(float32), HWC -> [1,3,H,W]."""
+    x = ((img_u8_hwc.astype(np.float64) / 255.0 - np.asarray(mean, dtype=np.float32).reshape(1, 1, 3)) /
+         np.asarray(std, dtype=np.float32).reshape(1, 1, 3)).astype(np.float32)
+    return torch.from_numpy(x.transpose(2, 0, 1)[None].copy())
+
+
+def warp_affine_bilinear(img_u8_hwc, inv_affine, H, W):
+    """Inverse-map bilinear warp with constant-0 border (the arithmetic cv2.warpAffine(INTER_LINEAR) approximates in
+    1/32-pixel fixed point; detector.py:399-407).  inv_affine: 2x3, network-input (x, y, 1) -> source (x, y).
+    Returns float64 [H,W,3] in [0,255]."""
+    A = np.asarray(inv_affine, dtype=np.float32).reshape(2, 3)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    sx = A[0, 0] * xs + A[0, 1] * ys + A[0, 2]
+    sy = A[1, 0] * xs + A[1, 1] * ys + A[1, 2]
+    x0, y0 = np.floor(sx).astype(np.int64), np.floor(sy).astype(np.int64)
+    lx, ly = (sx - np.floor(sx)).astype(np.float32), (sy - np.floor(sy)).astype(np.float32)
+    sh, sw, _ = img_u8_hwc.shape
+    img = img_u8_hwc.astype(np.float32)
+
+    def at(yy, xx):
+        ok = (yy >= 0) & (yy < sh) & (xx >= 0) & (xx < sw)
+        v = img[np.clip(yy, 0, sh - 1), np.clip(xx, 0, sw - 1)]
+        return v * ok[..., None]
+    top = at(y0, x0) + lx[..., None] * (at(y0, x0 + 1) - at(y0, x0))
+    bot = at(y0 + 1, x0) + lx[..., None] * (at(y0 + 1, x0 + 1) - at(y0 + 1, x0))
+    return top + ly[..., None] * (bot - top)

@@ -190,13 +190,14 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
     H, W, K, F = 96, 160, 20, 3
     frames = [spec.make_input((1, 3, H, W), tag=f"pipe{i}").to(dev) for i in range(7)]
     results = {}
-    for depth in (1, 2, 3):
+    for depth in (1, 2, 3, 4):                               # 4 = what bench.py runs
         m, sd, opt = build(heads, "mot", dev, max_object=32, K=K)
         pipe = FramePipeline(m, opt, H, W, mem_frames=F, device=dev, use_cuda_graph=graph, depth=depth)
         pipe.xs[0].copy_(frames[0])
         pipe.warmup()
-        pipe.memory.zero_()
-        pipe.head = 0
+        if graph:                                            # both halves of every arena are CUDA graphs
+            assert all(p.graph is not None for p in pipe.plans) and all(g is not None for g in pipe.tail_graph)
+        pipe.reset_memory()
         seq = []
         for x in frames:
             r = pipe.step_device(x)
@@ -211,7 +212,7 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
         torch.cuda.synchronize(dev)
         results[depth] = (seq, m, opt)
     seq1, m, opt = results[1]
-    for depth in (2, 3):
+    for depth in (2, 3, 4):
         for t, (a, b) in enumerate(zip(seq1, results[depth][0])):
             for k in a:
                 assert torch.equal(a[k], b[k]), (depth, t, k)
@@ -229,12 +230,17 @@ def test_frame_pipeline_depths_and_public_api_agree(dev, graph):
     centres = torch.stack([cx, cy], 1).view(1, K, 1, 1, 2)
     emb = m.AFE.forward_feature_extracter(fm, centres)
     assert nerr(emb[0].cpu(), seq1[0]["embeddings"].cpu()) < 1e-4
-    # frame 1's affinity: memory holds frame 0's embeddings in ring slot 0, zeros elsewhere
+    # frame 0 met an empty recorder: every block is zero.  Frame 1: the recorder holds frame 0's K embeddings in ring
+    # slot 0 (frame index 0), the other slots are still empty (no live rows -> zero blocks, not "zero embeddings")
+    assert float(seq1[0]["affinity"].abs().max()) == 0.0
     mem = torch.zeros((F, 32, emb.shape[2]), device=dev)
     mem[0, :K] = seq1[0]["embeddings"]
-    aff = m.AFE.affinity_batched(mem, [K] * F, seq1[1]["embeddings"].contiguous())
+    aff = m.AFE.affinity_batched(mem, [K] + [0] * (F - 1), seq1[1]["embeddings"].contiguous())
     assert aff.shape == seq1[1]["affinity"].shape
-    assert nerr(aff[:, :K, : K + 1].cpu(), seq1[1]["affinity"][:, :K, : K + 1].cpu()) < 1e-4
+    assert nerr(aff[0, :K, : K + 1].cpu(), seq1[1]["affinity"][0, :K, : K + 1].cpu()) < 1e-4
+    assert float(seq1[1]["affinity"][1:].abs().max()) == 0.0 and float(seq1[1]["affinity"][0, K:].abs().max()) == 0.0
+    # frame F+1 wraps the ring: every slot is live
+    assert float(seq1[F + 1]["affinity"][:, :K, :K].min()) > 0.0
 
 
 @pytest.mark.parametrize("name,heads,dataset,hw,K,F,lstm_tracks", [
@@ -262,8 +268,7 @@ def test_c3_c4_shapes_pipeline_properties(dev, name, heads, dataset, hw, K, F, l
             pipe.lstm_x.copy_(spec.make_input(tuple(pipe.lstm_x.shape), tag="lx").to(dev))
         pipe.xs[0].copy_(frames[0])
         pipe.warmup()
-        pipe.memory.zero_()
-        pipe.head = 0
+        pipe.reset_memory()
         if lstm_tracks:
             pipe.lstm_h.zero_()
             pipe.lstm_c.zero_()

@@ -1,0 +1,339 @@
+"""GPU parity tests added in round 2 (all through the C ABI):
+
+* BASELINE configs C2 / C3 / C4 at their FULL sizes, through FramePipeline(depth=4) -- the configuration bench.py
+  times -- against the CPU oracle (oracle/restate.py): every head, all 13 FeatureMaps, decode, embeddings of the decoded
+  detections, affinity against the full track memory, LSTM step (C3).
+* row a9: AFE_module.forward / loss against a golden produced by the REAL reference module (tests/golden/afe_train_forward.pt).
+* row f1: device-resident recorder + per-track decayed median against the restated tracker.py logic.
+* row f2: uint8 frame -> normalisation fused into the stem; affine warp pre-processing.
+* KalmanFilterLSTM(opt) constructor contract, no silent SIMT fallback on DLA-34 shapes.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, nerr
+from oracle import restate, spec
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # BASELINE.json: 1e-3 relative fp32
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch.device("cuda:0")
+
+
+def build(heads, dataset, dev, max_object=100, **kw):
+    from deft_b200.model.model import create_model
+    from deft_b200.opts import Opt
+    opt = Opt(dataset=dataset, max_object=max_object, heads=dict(heads), **kw)
+    m = create_model("dla_34", dict(heads), {h: [256] for h in heads}, opt).eval()
+    sd = spec.make_state_dict(spec.dlaseg_spec(heads, dataset=dataset))
+    m.load_state_dict(sd, strict=True)
+    return m.to(dev), sd, opt
+
+
+# BASELINE.json configs at their real sizes: (heads, dataset, (H, W), K, max_object, F, rows per memory
+# frame, LSTM tracks)
+FULL = {
+    "c2_mot_1088x608": (spec.MOT_HEADS, "mot", (608, 1088), 100, 100, 5, 100, 0),             # 100 dets x 5x100 = 500 tracks
+    "c3_kitti_1248x384": (spec.KITTI_HEADS, "kitti", (384, 1248), 50, 100, 4, 50, 200),       # 50 dets x 4x50 = 200 tracks + LSTM T=200
+    "c4_nuscenes_1632x928": (spec.NUSC_HEADS, "nuscenes", (928, 1632), 300, 300, 4, 250, 0),  # 300 dets x 4x250 = 1000 tracks, 704-d
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_size_frame_vs_oracle_depth4(dev, name):
+    from deft_b200 import _lib
+    from deft_b200.kalman_filter_lstm import DecoderRNN, KalmanFilterLSTM
+    from deft_b200.model.decode import generic_decode
+    from deft_b200.pipeline import FramePipeline
+    heads, dataset, (H, W), K, P, F, rows, T = FULL[name]
+    torch.set_num_threads(os.cpu_count() or 8)
+    fallbacks0 = _lib.lib().deft_simt_fallback_count()
+    m, sd, opt = build(heads, dataset, dev, max_object=P, K=K)
+    kf, lsd = None, None
+    if T:
+        lsd = spec.make_state_dict(spec.lstm_spec(dataset), seed=55)
+        rnn = DecoderRNN(128, dataset)
+        rnn.load_state_dict(lsd)
+        kf = KalmanFilterLSTM(opt, rnn.to(dev))
+    pipe = FramePipeline(m, opt, H, W, mem_frames=F, mem_rows=rows, lstm=kf, lstm_tracks=T, device=dev, depth=4)
+    cemb = pipe.cemb
+    x = spec.make_input((1, 3, H, W), tag=name)
+    others = [spec.make_input((1, 3, H, W), tag=f"{name}_o{i}") for i in range(2)]
+    mem = spec.make_input((F, rows, cemb), tag=name + "_mem").abs() * 0.5          # embeddings are ReLU outputs (>= 0)
+    pipe.xs[0].copy_(x.to(dev))
+    pipe.warmup()
+    assert all(p.graph is not None for p in pipe.plans) and all(g is not None for g in pipe.tail_graph)
+    pipe.prefill_memory(mem.to(dev))
+    if T:
+        h0, c0 = spec.make_input((T, 128), tag="fs_h") * 0.1, spec.make_input((T, 128), tag="fs_c") * 0.1
+        lx = spec.make_input((T, kf.model.fin), tag="fs_x")
+        pipe.lstm_h.copy_(h0.to(dev)); pipe.lstm_c.copy_(c0.to(dev)); pipe.lstm_x.copy_(lx.to(dev))
+    frames = [x.to(dev), others[0].to(dev), others[1].to(dev), x.to(dev)]
+    keys = ["scores", "clses", "bboxes", "xs", "ys", "embeddings", "affinity"] + (["lstm_pred"] if T else [])
+    snaps = []
+    for f in frames:                                           # four frames in flight, no host sync in between
+        r = pipe.step_device(f)
+        with torch.cuda.stream(pipe.tail_stream):
+            snaps.append({k: r[k].clone() for k in keys})
+    pipe.synchronize()
+    torch.cuda.synchronize(dev)
+    assert _lib.lib().deft_simt_fallback_count() == fallbacks0, "a DLA-34 / AFE layer silently dropped to the SIMT engine"
+    r0 = {k: v.cpu() for k, v in snaps[0].items()}
+    # arena 0 still holds frame 0 (4 arenas, 4 frames); arena 3 holds the same input again: identical bits
+    h_gpu = {k: v.clone() for k, v in pipe.plans[0].head_out.items()}
+    fm_gpu = [f.clone() for f in pipe.plans[0].fm_views]
+    for k in h_gpu:
+        assert torch.equal(h_gpu[k], pipe.plans[3].head_out[k]), k
+    for a, b in zip(fm_gpu, pipe.plans[3].fm_views):
+        assert torch.equal(a, b)
+    for k in ("scores", "clses", "bboxes", "embeddings"):
+        assert torch.equal(snaps[0][k], snaps[3][k]), k
+    # ---------------- oracle
+    with torch.no_grad():
+        ref_out, ref_fm = restate.dlaseg_forward(sd, x, heads)
+        sig = restate.sigmoid_output(ref_out[0], getattr(opt, "depth_scale", 1.0))
+        dref = restate.generic_decode(sig, K=K)
+    errs = {}
+    for h in heads:                                            # hm / dep were transformed in place by _sigmoid_output
+        errs[h] = nerr(h_gpu[h].cpu(), sig[h] if h in ("hm", "dep") else ref_out[0][h])
+    for i in range(13):
+        errs[f"fm{i}"] = nerr(fm_gpu[i].cpu(), ref_fm[i])
+    # decode: same detections wherever the score gap exceeds the network tolerance; bit-exact on the oracle's heat-map
+    assert nerr(r0["scores"], dref["scores"]) < 5 * TOL
+    gaps = (dref["scores"][0, :-1] - dref["scores"][0, 1:]).abs()
+    stable = torch.ones(K, dtype=torch.bool)
+    stable[:-1] &= gaps > 1e-4
+    stable[1:] &= gaps > 1e-4
+    stable[-1] = False
+    assert int(stable.sum()) > K // 2
+    assert torch.equal(r0["xs"][0][stable], dref["xs"][0][stable]) and torch.equal(r0["ys"][0][stable], dref["ys"][0][stable])
+    assert torch.equal(r0["clses"][0][stable].long(), dref["clses"][0][stable].long())
+    dshared = generic_decode({k: v.to(dev) for k, v in sig.items()}, K=K, opt=opt)
+    for k in ("scores", "clses", "xs", "ys", "bboxes"):
+        assert torch.equal(dshared[k].cpu(), dref[k]), k
+    # embeddings of the decoded detections (oracle extractor on the oracle's FeatureMaps at the GPU's centres)
+    oh, ow = H // 4, W // 4
+    with torch.no_grad():
+        centres = restate.convert_detection(r0["bboxes"][0].numpy(), oh, ow)
+        e_ref = restate.afe_extract(sd, ref_fm, centres)
+        errs["emb"] = nerr(r0["embeddings"], e_ref[0])
+        # affinity of the K detections against every memory frame (the reference's per-frame call, tracker.py:76-90)
+        worst = 0.0
+        for f in range(F):
+            a_ref = restate.afe_affinity(sd, mem[f:f + 1], r0["embeddings"][None], P, False)
+            worst = max(worst, nerr(r0["affinity"][f, :rows, : K + 1], a_ref))
+        errs["aff"] = worst
+        assert float(r0["affinity"][:, rows:].abs().max()) == 0.0 if rows < P else True
+        if T:
+            rh, rc, rp = restate.lstm_predict(lsd, h0, c0, lx, kf.MAX_dis_fut)
+            errs["lstm"] = nerr(r0["lstm_pred"], rp)
+        # end to end (oracle's own detections -> its own embeddings), wherever both sides decoded the same peak
+        e_own = restate.afe_extract(sd, ref_fm, restate.convert_detection(dref["bboxes"][0].numpy(), oh, ow))[0]
+        same = (r0["xs"][0] == dref["xs"][0]) & (r0["ys"][0] == dref["ys"][0]) & (r0["clses"][0].long() == dref["clses"][0].long())
+        assert int(same.sum()) >= int(stable.sum())
+        errs["emb_e2e"] = nerr(r0["embeddings"][same], e_own[same])
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()}, f"stable={int(stable.sum())}/{K} same={int(same.sum())}/{K}")
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------------ a9
+def test_afe_forward_and_loss_vs_reference_golden(dev):
+    """AFE_module.forward (AFE.py:74-86) + add_unmatched_dim (215-233) + loss (235-328): golden = the REAL reference
+    module run in the build container (oracle/gen_golden.py::gen_afe_train), B=2, P=100."""
+    from oracle.gen_golden import afe_train_inputs
+    g = torch.load(os.path.join(GOLDEN, "afe_train_forward.pt"), weights_only=False)
+    B, P = g["meta"]["B"], g["meta"]["P"]
+    for tensor_core, tol in ((False, 5e-5), (True, TOL)):
+        m, sd, opt = build(spec.MOT_HEADS, "mot", dev, max_object=P, tensor_core=tensor_core)
+        fm_pre, fm_next, l_pre, l_next, target, mask0, mask1 = afe_train_inputs(B, P)
+        to = lambda ts: [t.to(dev) for t in ts]
+        x = m.AFE(to(fm_pre), to(fm_next), l_pre.to(dev), l_next.to(dev))
+        assert x.shape == g["x"].shape == (B, 1, P + 1, P + 1)
+        e = nerr(x.cpu(), g["x"])
+        assert torch.equal(x[:, :, P, :].cpu(), torch.ones(B, 1, P + 1)) and torch.equal(x[:, :, :, P].cpu(), torch.ones(B, 1, P + 1))
+        # loss on the reference's own score matrix (shared input): every scalar, and the argmax indices exactly
+        res = m.AFE.loss(g["x"].to(dev), target.to(dev), mask0.to(dev), mask1.to(dev))
+        vals = [float(v) for v in res[:7]]
+        for a, b in zip(vals, g["loss"]):
+            assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (vals, g["loss"])
+        assert torch.equal(res[7].cpu(), g["indexes_pre"])
+        # loss on OUR score matrix: the scalars within the network tolerance
+        res2 = m.AFE.loss(x, target.to(dev), mask0.to(dev), mask1.to(dev))
+        for a, b in zip([float(v) for v in res2[:4]], g["loss"][:4]):
+            assert abs(a - b) <= 5 * tol * max(1.0, abs(b))
+        print("a9", "tc" if tensor_core else "simt", f"forward nerr={e:.2e}", [f"{v:.6f}" for v in vals])
+        assert e < tol
+    # degenerate masks: nothing selected -> the reference's "+ 1" accuracies and un-normalised sums
+    z = torch.zeros(B, 1, P + 1, dtype=torch.uint8)
+    with torch.no_grad():
+        ref_vals, ref_idx = restate.afe_loss(g["x"], target, z, z, P)
+    res = m.AFE.loss(g["x"].to(dev), target.to(dev), z.to(dev), z.to(dev))
+    for a, b in zip([float(v) for v in res[:7]], ref_vals):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b))
+
+
+# ------------------------------------------------------------------------------------------------ f1
+def _oracle_tracks(aff, counts, slot_frame, clock, nodes, m, dataset):
+    """restate.recorder_similarity + track_similarity over the recorder state -> sim [T, m+1] (zeros when None)."""
+    F = aff.shape[0]
+    by_frame = {}
+    for s in range(F):
+        fr = int(slot_frame[s])
+        if fr >= 0 and fr < clock:
+            by_frame[fr] = aff[s, : int(counts[s]), : m + 1].numpy()
+    allsim = restate.recorder_similarity(by_frame, clock, dataset=dataset)
+    out = np.zeros((len(nodes), m + 1), dtype=np.float32)
+    for t, nl in enumerate(nodes):
+        usable = [(f, i) for f, i in nl if f in allsim and i < allsim[f].shape[0]]
+        s = restate.track_similarity(usable, clock, allsim, dataset=dataset)
+        if s is not None:
+            out[t] = s
+    return out
+
+
+@pytest.mark.parametrize("dataset,F", [("mot", 7), ("nuscenes", 5), ("kitti_tracking", 8)])
+def test_track_similarity_op_vs_restated_tracker(dev, dataset, F):
+    """deft_track_similarity against tracker.py:76-90 (decay) + 219-252 (median over the last mm rows; exactly mm+1 rows are
+    all kept), bit for bit, on random recorder states: empty slots, overwritten frames, 0..6 nodes per track."""
+    from deft_b200 import _lib, ops
+    rng = np.random.RandomState(7 + F)
+    P, m, T = 24, 17, 64
+    L = _lib.lib().deft_track_nodes_per_track()
+    mm = 2 if dataset == "nuscenes" else 4
+    m_frame = {"kitti_tracking": 5, "nuscenes": 3}.get(dataset, 10)
+    for clock in (0, 3, F + 2, 40):
+        aff = torch.rand((F, P, P + 1), generator=torch.Generator().manual_seed(clock + 1))
+        slot_frame = np.full(F, -1, dtype=np.int32)
+        counts = np.zeros(F, dtype=np.int32)
+        for fr in range(max(0, clock - F), clock):            # the ring holds the last F frames (one left empty now and then)
+            if fr % 5 == 4:
+                continue
+            slot_frame[fr % F] = fr
+            counts[fr % F] = rng.randint(1, P + 1)
+        nodes = []
+        nf = np.full((T, L), -1, dtype=np.int32); ni = np.zeros((T, L), dtype=np.int32); nc = np.zeros(T, dtype=np.int32)
+        for t in range(T):
+            k = rng.randint(0, L + 1)
+            frs = sorted(rng.choice(np.arange(max(0, clock - F - 3), max(clock, 1)), size=min(k, max(clock, 1)), replace=False).tolist()) if clock else []
+            nl = [(int(f), int(rng.randint(0, P))) for f in frs]
+            nodes.append(nl)
+            nc[t] = len(nl)
+            for q, (f, i) in enumerate(nl):
+                nf[t, q], ni[t, q] = f, i
+        # the oracle sees what the reference's recorder would hold: nodes whose frame is gone / whose row is not live are unusable
+        usable_nodes = [[(f, i) for f, i in nl if f < clock and slot_frame[f % F] == f and i < counts[f % F]] for nl in nodes]
+        ref = _oracle_tracks(aff, counts, slot_frame, clock, usable_nodes, m, dataset)
+        d = lambda a, dt=torch.int32: torch.as_tensor(a).to(dt).to(dev)
+        sim = torch.full((T, P + 1), -1.0, device=dev)
+        cost = torch.full((T, P), -1.0, device=dev)
+        ops.track_similarity(aff.to(dev), d([clock, 0]), d(slot_frame), d(counts), d(nf), d(ni), d(nc), m, mm, m_frame, sim, cost)
+        torch.cuda.synchronize()
+        assert np.array_equal(sim[:, : m + 1].cpu().numpy(), ref), (dataset, clock)
+        assert np.array_equal(cost[:, :m].cpu().numpy(), (1.0 - ref[:, :m].astype(np.float64)).astype(np.float32))
+        assert float(sim[:, m + 1:].abs().max()) == 0.0 and float(cost[:, m:].abs().max()) == 0.0
+
+
+def test_pipeline_track_memory_sequence(dev):
+    """8-frame sequence through FramePipeline(tracks=T): after every frame the device-side cost matrix equals the
+    restated recorder + STrack.get_similarity run on the same affinity blocks, with synthetic associations appended
+    through append_matches; the recorder ring wraps (F=3 < 8 frames)."""
+    from deft_b200.pipeline import FramePipeline
+    heads = spec.MOT_HEADS
+    H, W, K, F, T, P = 96, 160, 12, 3, 10, 16
+    m, sd, opt = build(heads, "mot", dev, max_object=P, K=K)
+    pipe = FramePipeline(m, opt, H, W, mem_frames=F, device=dev, depth=1, tracks=T)
+    frames = [spec.make_input((1, 3, H, W), tag=f"trk{i}").to(dev) for i in range(8)]
+    pipe.xs[0].copy_(frames[0])
+    pipe.warmup()
+    pipe.reset_memory()
+    nodes = [[] for _ in range(T)]
+    slot_frame = np.full(F, -1, dtype=np.int32)
+    counts = np.zeros(F, dtype=np.int32)
+    for t, x in enumerate(frames):
+        r = pipe.step_device(x)
+        pipe.synchronize()
+        aff = r["affinity"].cpu()
+        usable = [[(f, i) for f, i in nl[-6:] if slot_frame[f % F] == f] for nl in nodes]     # the device keeps the newest 6 nodes
+        ref = _oracle_tracks(aff, counts, slot_frame, t, usable, K, "mot")
+        assert np.array_equal(r["similarity"][:, : K + 1].cpu().numpy(), ref), t
+        assert np.array_equal(r["cost"][:, :K].cpu().numpy(), (1.0 - ref[:, :K].astype(np.float64)).astype(np.float32)), t
+        assert int(pipe.clock[0]) == t + 1 and int(pipe.slot_frame[t % F]) == t and int(pipe.counts[t % F]) == K
+        slot_frame[t % F] = t
+        counts[t % F] = K
+        match = np.array([(3 * k + t) % K if (k + t) % 4 else -1 for k in range(T)], dtype=np.int32)
+        pipe.append_matches(torch.from_numpy(match))
+        for k in range(T):
+            if match[k] >= 0:
+                nodes[k].append((t, int(match[k])))
+    assert ref.max() > 0                                       # the last frames really had usable nodes
+
+
+# ------------------------------------------------------------------------------------------------ f2
+def test_uint8_frame_fused_normalisation_and_warp(dev):
+    """Row f2: a uint8 HWC frame through the u8 stem equals the reference's pre-processing (detector.py:408-410,
+    restate.normalize_u8) followed by the fp32 path; the affine warp kernel equals the restated bilinear warp."""
+    from deft_b200 import ops
+    heads = spec.MOT_HEADS
+    H, W = 96, 160
+    mean, std = [0.408, 0.447, 0.470], [0.289, 0.274, 0.278]   # the reference's default dataset statistics
+    m, sd, opt = build(heads, "mot", dev)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (1, H, W, 3), generator=g, dtype=torch.uint8)
+    x_ref = restate.normalize_u8(img[0].numpy(), mean, std)
+    out_f, fm_f = m(x_ref.to(dev))
+    h_f = {k: v.clone() for k, v in out_f[0].items()}
+    p8 = m.plan_for_shape(1, H, W, dev, u8_norm=(mean, std))
+    heads8, fm8 = p8.run(img.to(dev))
+    torch.cuda.synchronize()
+    for k in h_f:
+        assert nerr(heads8[k].cpu(), h_f[k].cpu()) < 1e-5, k
+    with torch.no_grad():
+        ref_out, _ = restate.dlaseg_forward(sd, x_ref, heads)
+    for k in h_f:
+        assert nerr(heads8[k].cpu(), ref_out[0][k]) < TOL, k
+    # affine warp (keep-resolution crop/scale of a larger source frame, detector.py:386-407)
+    src = torch.randint(0, 256, (70, 110, 3), generator=g, dtype=torch.uint8)
+    for inv in ([1.0, 0.0, 0.0, 0.0, 1.0, 0.0], [0.71, 0.05, -3.3, -0.04, 0.69, 2.6], [1.9, 0.0, 10.2, 0.0, 1.9, -6.5]):
+        got = ops.preprocess_warp(src.to(dev), inv, mean, std, 64, 96)
+        ref = restate.normalize_u8(np.zeros((1, 1, 3), dtype=np.uint8), mean, std)   # shape helper only
+        warped = restate.warp_affine_bilinear(src.numpy(), inv, 64, 96)
+        ref = ((torch.from_numpy(warped).float() / 255.0 - torch.tensor(mean)) / torch.tensor(std)).permute(2, 0, 1)[None]
+        assert float((got.cpu() - ref).abs().max()) < 2e-4, inv
+    ident = ops.preprocess_warp(src.to(dev), [1.0, 0.0, 0.0, 0.0, 1.0, 0.0], mean, std, 70, 110)
+    assert nerr(ident.cpu(), restate.normalize_u8(src.numpy(), mean, std)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ ADVICE r1
+def test_kalman_filter_lstm_constructor_contract(dev, tmp_path):
+    """KalmanFilterLSTM(opt) like tracker.py:144 builds it: loads opt.load_model_traj through load_model, moves the model to
+    opt.device and switches to eval (kalman_filter_lstm.py:50-62).  A model left on the CPU is refused, not dereferenced."""
+    from deft_b200._lib import DeftError
+    from deft_b200.kalman_filter_lstm import DecoderRNN, KalmanFilterLSTM
+    from deft_b200.model.model import save_model
+    from deft_b200.opts import Opt
+    lsd = spec.make_state_dict(spec.lstm_spec("mot"), seed=55)
+    rnn = DecoderRNN(128, "mot")
+    rnn.load_state_dict(lsd)
+    path = str(tmp_path / "traj.pth")
+    save_model(path, 3, rnn)
+    opt = Opt(dataset="mot", load_model_traj=path)
+    opt.device = dev
+    kf = KalmanFilterLSTM(opt)
+    assert next(kf.model.parameters()).device == dev and not kf.model.training
+    h0, c0, x = spec.make_input((1, 1, 128), tag="kh") * 0.1, spec.make_input((1, 1, 128), tag="kc") * 0.1, spec.make_input((1, 1, 11), tag="kx")
+    hn, cn, pred = kf.predict(h0.to(dev), c0.to(dev), x.to(dev))
+    rh, rc, rp = restate.lstm_predict(lsd, h0.view(1, 128), c0.view(1, 128), x.view(1, 11), 5)
+    assert nerr(hn.cpu().view(1, 128), rh) < 1e-5 and sorted(pred) == [1, 2, 3, 4, 5]
+    assert nerr(np.stack([pred[i + 1] for i in range(5)]), rp[0]) < 1e-5
+    cpu_model = KalmanFilterLSTM(Opt(dataset="mot"), DecoderRNN(128, "mot"))          # injected, never moved
+    with pytest.raises(DeftError):
+        cpu_model.predict(h0.to(dev), c0.to(dev), x.to(dev))

@@ -158,3 +158,34 @@ def test_packing_algebra():
     X = torch.zeros(101, 101); X[:4, :3] = S; X[100, :] = 1; X[:, 100] = 1
     mine = torch.max(torch.softmax(X, 1), torch.softmax(X, 0))[:4, :3]
     assert nerr(mine, ref[:, :3]) < 1e-5
+
+
+def test_load_model_reset_hm_and_reuse_hm(tmp_path, capsys):
+    """model.py:58-77: with opt.reset_hm an `hm*` tensor whose leading dimension is 80 (COCO) or 1 (CrowdHuman) is treated as a
+    mismatch even when the shapes agree (-> skipped); with opt.reuse_hm a mismatched tensor's leading slice is reused."""
+    import torch
+    from types import SimpleNamespace
+    from deft_b200.model.model import _reconcile
+    own = {"hm.2.weight": torch.zeros(1, 256, 1, 1), "hm.2.bias": torch.zeros(1), "wh.2.bias": torch.zeros(2)}
+    ck = {"hm.2.weight": torch.ones(1, 256, 1, 1), "hm.2.bias": torch.ones(1), "wh.2.bias": torch.ones(2)}
+    merged, rep = _reconcile(ck, own)
+    assert merged["hm.2.bias"].item() == 1 and not rep
+    merged, rep = _reconcile(ck, own, reset_hm=True)
+    assert merged["hm.2.bias"].item() == 0 and merged["hm.2.weight"].sum().item() == 0 and merged["wh.2.bias"].sum().item() == 2
+    assert sum("Skip loading parameter hm" in r for r in rep) == 2
+    coco = {"hm.2.weight": torch.arange(80.).view(80, 1, 1, 1).repeat(1, 256, 1, 1), "hm.2.bias": torch.arange(80.)}
+    merged, rep = _reconcile(coco, own, reuse_hm=True)
+    assert merged["hm.2.bias"].tolist() == [0.0] and merged["hm.2.weight"].shape == (1, 256, 1, 1)
+    assert all("Reusing parameter" in r for r in rep[:2])
+
+
+def test_bench_stream_assignment_for_the_nuscenes_split():
+    """BASELINE config C4: 6 cameras dealt round-robin over 2/4/8 GPUs; every stream is owned exactly once."""
+    from deft_b200.parallel import stream_assignment
+    for world in (1, 2, 4, 8):
+        owned = [stream_assignment(6, world, r) for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(6))
+        assert max(len(o) for o in owned) == -(-6 // world)
+    import bench
+    nf, ni, nc = bench.synthetic_tracks(500, 5, 100, 6, 5)
+    assert int(nc.min()) == 1 and int(nc.max()) == 5 and int(nf[nf >= 0].min()) == 0 and int(nf.max()) == 4

@@ -136,3 +136,57 @@ def test_live_reference_affinity_depends_on_max_object():
         ref = mod.forward_stacker_features(xp, xn, False)
     assert np.abs(a - b).max() > 1e-3
     assert nerr(b, ref) < 1e-5
+
+
+def test_afe_train_forward_and_loss_restatement_vs_reference_golden():
+    """Row a9: restate.afe_forward / afe_loss against the REAL AFE_module.forward / .loss (golden produced by
+    oracle/gen_golden.py::gen_afe_train in the build container)."""
+    from oracle.gen_golden import afe_train_inputs
+    g = torch.load(os.path.join(GOLDEN, "afe_train_forward.pt"), weights_only=False)
+    B, P = g["meta"]["B"], g["meta"]["P"]
+    sd = spec.make_state_dict(spec.dlaseg_spec(spec.MOT_HEADS))
+    fm_pre, fm_next, l_pre, l_next, target, mask0, mask1 = afe_train_inputs(B, P)
+    with torch.no_grad():
+        x = restate.afe_forward(sd, fm_pre, fm_next, l_pre, l_next, P)
+        vals, idx = restate.afe_loss(g["x"], target, mask0, mask1, P)
+    assert nerr(x, g["x"]) < 2e-5
+    assert np.allclose(vals, g["loss"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(idx, g["indexes_pre"])
+
+
+def test_track_similarity_restatement_properties():
+    """Row f1 oracle (the tracker module itself cannot be imported: SURVEY 8(c)): the restated get_similarity keeps the
+    reference's row-selection quirk (exactly mm+1 rows -> all of them, more -> the last mm) and its decay rule."""
+    rng = np.random.RandomState(0)
+    sims = {f: rng.rand(5, 8).astype(np.float32) for f in range(10)}
+    rec = restate.recorder_similarity(sims, 10, dataset="mot")
+    assert all(np.array_equal(rec[f], sims[f]) for f in range(1, 10))                        # decay = 1.0 inside m_frame = 10
+    assert np.array_equal(rec[0], (sims[0] * pow(0.01, 10 / 3.0)).astype(np.float32))         # beyond: decay2 ** (d/3)
+    nodes = [(f, f % 5) for f in range(3, 10)]
+    rows = np.array([rec[f][i] for f, i in nodes])
+    assert np.array_equal(restate.track_similarity(nodes[-4:], 10, rec), np.median(rows[-4:], axis=0))
+    assert np.array_equal(restate.track_similarity(nodes[-5:], 10, rec), np.median(rows[-5:], axis=0))   # mm+1 rows: all five
+    assert np.array_equal(restate.track_similarity(nodes, 10, rec), np.median(rows[-4:], axis=0))        # seven rows: the last four
+    assert restate.track_similarity([], 10, rec) is None
+    assert np.array_equal(restate.track_similarity(nodes[-3:], 10, rec, dataset="nuscenes"), np.median(rows[-3:], axis=0))
+    assert np.array_equal(restate.track_similarity(nodes[-4:], 10, rec, dataset="nuscenes"), np.median(rows[-2:], axis=0))
+
+
+def test_preprocess_restatement_vs_cv2():
+    """Row f2 oracle: the restated bilinear warp stays within cv2.warpAffine's 1/32-pixel fixed-point error (the
+    reference calls cv2: detector.py:399-407); the normalisation is detector.py:408-410 verbatim."""
+    cv2 = pytest.importorskip("cv2")
+    g = torch.Generator().manual_seed(5)
+    src = torch.randint(0, 256, (70, 110, 3), generator=g, dtype=torch.uint8).numpy()
+    # smooth the source: the fixed-point coordinate error is bounded per unit of gradient
+    src = cv2.GaussianBlur(src, (7, 7), 2.0)
+    fwd = np.array([[1.3, 0.05, 4.0], [-0.03, 1.25, -2.0]], dtype=np.float32)               # trans_input: source -> network input
+    inv = cv2.invertAffineTransform(fwd)
+    ref = cv2.warpAffine(src, fwd, (96, 64), flags=cv2.INTER_LINEAR).astype(np.float64)
+    got = restate.warp_affine_bilinear(src, inv, 64, 96)
+    inner = (got > 0).all(axis=2)
+    assert np.abs(got - ref)[inner].max() <= 4.0                                             # of 255: coordinate quantisation x gradient
+    assert np.abs(got - ref)[inner].mean() < 0.6
+    x = restate.normalize_u8(src, [0.408, 0.447, 0.470], [0.289, 0.274, 0.278])
+    assert x.shape == (1, 3, 70, 110) and x.dtype == torch.float32
+    assert abs(float(x[0, 1, 3, 4]) - ((src[3, 4, 1] / 255.0 - 0.447) / 0.274)) < 1e-6

@@ -2,13 +2,13 @@
 
 Each case runs in its own subprocess so a trapped kernel cannot poison the others; prints the
 normalised max error of the tensor-core path (3xTF32 and 1xTF32) against the fp32 SIMT engine on the
-same GPU, plus a small dump on mismatch.   python tests/tc_diag.py [case ...]
+same GPU, plus a small dump on mismatch.   python tools/tc_diag.py [case ...]
 """
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ sits next to deft_b200/
 sys.path.insert(0, ROOT)
 
 CASES = {

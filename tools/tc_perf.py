@@ -1,7 +1,7 @@
 """Perf bring-up for the tcgen05 engine (GPU box; not a pytest file): times single layers with CUDA events.
-   DEFT_TC_DBG=<bits> python tests/tc_perf.py   (bits: 1 no B copy, 2 no A loads, 4 no A stores, 8 no MMA, 16 no epilogue)"""
+   DEFT_TC_DBG=<bits> python tools/tc_perf.py   (bits: 1 no B copy, 2 no A loads, 4 no A stores, 8 no MMA, 16 no epilogue)"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ sits next to deft_b200/
 sys.path.insert(0, ROOT)
 import torch
 from deft_b200 import ops, packing
@@ -11,6 +11,8 @@ dev = torch.device("cuda:0")
 CASES = [("c3x3 64->64 @152x272", "conv", 64, 64, 3, 152, 272), ("c1x1 64->64 @152x272", "conv", 64, 64, 1, 152, 272),
          ("c3x3 128->128 @76x136", "conv", 128, 128, 3, 76, 136), ("c3x3 256->256 @38x68", "conv", 256, 256, 3, 38, 68),
          ("dcn 64->64 @152x272", "dcn", 64, 64, 3, 152, 272), ("dcn 128->64 @76x136", "dcn", 128, 64, 3, 76, 136),
+         ("dcn 128->128 @76x136", "dcn", 128, 128, 3, 76, 136), ("dcn 256->256 @38x68", "dcn", 256, 256, 3, 38, 68),
+         ("dcn 256->128 @38x68", "dcn", 256, 128, 3, 38, 68),
          ("heads mot @152x272", "heads", 64, 0, 3, 152, 272)]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 for name, kind, cin, cout, k, H, W in CASES:

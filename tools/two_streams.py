@@ -1,6 +1,6 @@
 """Experiment (GPU box; not a pytest file): aggregate frame rate of S independent FramePipelines on S CUDA streams of one GPU."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ sits next to deft_b200/
 sys.path.insert(0, ROOT)
 import torch
 import bench
