@@ -220,7 +220,8 @@ def build_pipeline(args, cfg, dev, seed, torch):
         kf = KalmanFilterLSTM(opt, rnn.to(dev))
     pipe = FramePipeline(model, opt, cfg["H"], cfg["W"], mem_frames=cfg["F"], mem_rows=cfg["rows"], lstm=kf, lstm_tracks=cfg["lstm"], device=dev,
                          use_cuda_graph=not args.no_graph, depth=args.depth, dense_streams=args.dense_streams,
-                         tracks=0 if args.no_tracks else cfg["tracks"], uint8_norm=None if args.fp32_input else (MEAN, STD))
+                         tracks=0 if args.no_tracks else cfg["tracks"], uint8_norm=None if args.fp32_input else (MEAN, STD),
+                         assign_thresh=0.9 if args.assign else None)
     return model, pipe, opt
 
 
@@ -359,7 +360,7 @@ def gpu_arm(args, rank, local_rank, world):
                 "config": {"workload": cfg["name"], "streams_total": n_total_streams, "streams_per_gpu": S if world == 1 or not args.streams else f"{n_total_streams} streams round-robin over {world} GPUs",
                            "parallelism": f"stream-parallel, {n_total_streams} stream(s) over {world} GPU(s) (no collective)",
                            "cuda_graph": not args.no_graph, "input": "fp32 NCHW (pre-normalised)" if args.fp32_input else "uint8 HWC, normalisation fused into the stem",
-                           "track_reduction": (not args.no_tracks) and cfg["tracks"],
+                           "track_reduction": (not args.no_tracks) and cfg["tracks"], "device_assignment": bool(args.assign),
                            "frame_pipelining": f"{pipes[0].depth} frames of a stream in flight: {pipes[0].S} dense stream(s) + 1 tail stream (results bit-identical to depth 1, delivered in frame order)",
                            "l2": "no flush: inputs larger than L2 (~1 GB of unique weights + activations per frame vs 126 MB L2, rotating input frames)",
                            "engine": "simt-fp32" if args.simt else "tcgen05"},
@@ -427,7 +428,7 @@ def cpu_leg_with_parity(args, cfg, model, pipe, dev, torch):
     same = int(((res["xs"][0].cpu() == dref["xs"][0]) & (res["ys"][0].cpu() == dref["ys"][0])).sum())
     out["parity"] = {"max_nerr": max(errs.values()), "worst": max(errs, key=errs.get), "decode_exact": bool(decode_exact),
                      "same_detections": f"{same}/{cfg['K']}", "tolerance": 1e-3, "through": f"FramePipeline(depth={pipe.depth}), same weights and frame as the cpu_baseline leg",
-                     "tensors": len(errs)}
+                     "tensors": len(errs), "nerr": {k: float("%.3g" % v) for k, v in errs.items()}}
     return out
 
 
@@ -444,6 +445,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--fp32-input", action="store_true", help="pre-normalised fp32 NCHW frames (round-1 input path) instead of uint8 HWC")
     ap.add_argument("--no-tracks", action="store_true", help="skip the per-track similarity reduction (D2H = raw affinity blocks, as in round 1)")
+    ap.add_argument("--assign", action="store_true", help="row f3: run the linear assignment (thresh 0.9) + node append on the device; D2H = matches only")
     ap.add_argument("--depth", type=int, default=4, choices=[1, 2, 3, 4], help="FramePipeline: activation arenas = frames of the stream in flight")
     ap.add_argument("--dense-streams", type=int, default=None, help="FramePipeline: CUDA streams the dense parts rotate over (default depth - 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

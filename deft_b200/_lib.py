@@ -70,10 +70,16 @@ _SIGS = {
                                         C.c_int, C.c_double, C.c_double, c_fp, c_fp, c_fp]),
     "deft_track_append": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp, c_fp]),
     "deft_count_above": (C.c_int, [c_fp, C.c_int, C.c_float, c_fp, c_fp]),
+    "deft_assign_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "deft_fuse_and_assign": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_double, C.c_double, c_fp, c_fp, c_fp, C.c_size_t,
+                                       c_fp]),
     "deft_stem_conv7x7_u8": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), c_fp, c_fp, c_fp, c_fp, C.c_int,
                                        c_fp, c_fp]),
     "deft_preprocess_warp": (C.c_int, [c_fp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), c_fp, C.c_int,
                                        C.c_int, c_fp]),
+    "deft_dcnv2_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "deft_dcnv2_backward": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_int, C.c_int, c_fp, C.c_int, c_fp,
+                                      C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
     "deft_lstm_step": (C.c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int, C.c_int, C.c_int,
                                  c_fp, c_fp, c_fp, c_fp]),
 }

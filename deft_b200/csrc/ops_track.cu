@@ -6,6 +6,7 @@
 //   a9  AFE_module.loss forward (AFE.py:235-328): masked dual-softmax cross-entropy + consistency + accuracies.
 // All SIMT fp32: these are latency / HBM-bound element and reduction kernels, not GEMMs.
 #include "common.cuh"
+#include <math_constants.h>
 
 namespace deft {
 
@@ -479,6 +480,138 @@ __global__ void __launch_bounds__(256) loss_final_kernel(LossArgs a) {
     }
 }
 
+
+// ================================================================================================ f3
+// Motion fusion (matching.py:311-364, the LSTM branch the tracker takes: tracker.py:903-913) and the linear assignment
+// (matching.py:40-55: lap.lapjv(cost, extend_cost=True, cost_limit=thresh)) on the device.
+//
+// fuse_motion, use_lstm=True, only_position=True: for a track with >= 300 observations the gate is the squared
+// distance between the detection centre and the track's predicted centre (covariance = identity, tracker.py:200):
+// cost = inf where d2 > 5 * chi2inv95[2], then cost = lambda * cost + 0.05 * (1 - lambda) * d2.  For younger tracks the
+// reference asks for metric="gaussian", whose slice [3:-1] of a 2-vector is empty (kalman_filter_lstm.py:91-94), so the
+// gating distance is identically 0 and the row is just lambda * cost.  Both are restated, quirk included.
+//
+// lapjv with extend_cost/cost_limit solves  min sum_matched c_ij + (limit/2) (#unmatched rows + #unmatched cols)
+// == every detection is either matched to a distinct track at c - limit or stays unmatched at 0.  Solved exactly in
+// fp64 by shortest augmenting paths with potentials (one detection row at a time; the column scan and the arg-min of
+// every Dijkstra step run across the block), which visits the same optimum as lapjv (unique for generic costs).
+__global__ void fuse_motion_kernel(const float* __restrict__ cost, int ldc, int T, int m, const int* __restrict__ m_dev, const float* __restrict__ pred_xy,
+                                   const int* __restrict__ n_obs, const float* __restrict__ det_xy, double lambda, double gate, int min_obs,
+                                   double limit, double* __restrict__ out, int ldT) {
+    DEFT_PDL_PROLOGUE();
+    const int mm = m_dev ? min(max(__ldg(m_dev), 0), m) : m;
+    const size_t total = (size_t)mm * T;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / T), t = (int)(idx - (size_t)i * T);
+        double c = (double)cost[(size_t)t * ldc + i];
+        if (pred_xy != nullptr) {
+            double d2 = 0.0;
+            if (n_obs[t] >= min_obs) {
+                const double dx = (double)det_xy[2 * i] - (double)pred_xy[2 * t], dy = (double)det_xy[2 * i + 1] - (double)pred_xy[2 * t + 1];
+                d2 = dx * dx + dy * dy;
+                if (d2 > gate) c = CUDART_INF;
+                c = lambda * c + 0.05 * (1.0 - lambda) * d2;
+            } else {
+                c = lambda * c + 0.0005 * (1.0 - lambda) * 0.0;
+            }
+        }
+        out[(size_t)i * ldT + t] = c - limit;             // shifted: matching is worth it iff < 0 (a dummy costs 0)
+    }
+}
+
+__global__ void __launch_bounds__(1024) assign_kernel(const double* __restrict__ cs, int ldT, int T, int m, const int* __restrict__ m_dev,
+                                                      int* __restrict__ match_track, int* __restrict__ match_det) {
+    DEFT_PDL_PROLOGUE();
+    extern __shared__ unsigned char asm_[];
+    const int mm = m_dev ? min(max(__ldg(m_dev), 0), m) : m;
+    double* v = reinterpret_cast<double*>(asm_);
+    double* minv = v + T;
+    double* u = minv + T;
+    int* p = reinterpret_cast<int*>(u + m);
+    int* way = p + T;
+    unsigned char* used = reinterpret_cast<unsigned char*>(way + T);
+    __shared__ double r_val[32];
+    __shared__ int r_idx[32];
+    __shared__ double s_delta, s_minvD, s_ui0;
+    __shared__ int s_j1, s_wayD, s_j0, s_done, s_isD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int t = tid; t < T; t += blockDim.x) { v[t] = 0.0; p[t] = -1; }
+    for (int i = tid; i < m; i += blockDim.x) u[i] = 0.0;
+    __syncthreads();
+    for (int i0 = 0; i0 < mm; ++i0) {
+        for (int t = tid; t < T; t += blockDim.x) { minv[t] = CUDART_INF; used[t] = 0; way[t] = -1; }
+        if (tid == 0) { s_minvD = CUDART_INF; s_wayD = -2; s_j0 = -1; s_done = 0; s_ui0 = 0.0; }
+        __syncthreads();
+        while (true) {
+            const int j0 = s_j0;
+            const int i = (j0 < 0) ? i0 : p[j0];
+            const double ui = u[i] + ((i == i0) ? 0.0 : 0.0);
+            // candidates of row i: every unused track column, and the row's private dummy (cost 0, potential 0)
+            double best = CUDART_INF;
+            int bidx = 0x7fffffff;
+            const double* row = cs + (size_t)i * ldT;
+            for (int t = tid; t < T; t += blockDim.x) {
+                if (used[t]) continue;
+                const double cur = row[t] - ui - v[t];
+                if (cur < minv[t]) { minv[t] = cur; way[t] = j0; }
+                if (minv[t] < best) { best = minv[t]; bidx = t; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+            }
+            if (lane == 0) { r_val[warp] = best; r_idx[warp] = bidx; }
+            __syncthreads();
+            if (tid == 0) {
+                double b = CUDART_INF; int bi = 0x7fffffff;
+                for (int w = 0; w < nw; ++w) if (r_val[w] < b || (r_val[w] == b && r_idx[w] < bi)) { b = r_val[w]; bi = r_idx[w]; }
+                const double candD = 0.0 - ui;
+                if (candD < s_minvD) { s_minvD = candD; s_wayD = j0; }
+                if (s_minvD <= b) { s_delta = s_minvD; s_isD = 1; s_j1 = -1; }     // the dummy wins ties: no match at cost == limit
+                else { s_delta = b; s_isD = 0; s_j1 = bi; }
+            }
+            __syncthreads();
+            const double delta = s_delta;
+            // potentials: visited columns (and the virtual start column holding i0) move by delta, the rest get closer
+            for (int t = tid; t < T; t += blockDim.x) {
+                if (used[t]) { u[p[t]] += delta; v[t] -= delta; }
+                else minv[t] -= delta;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                u[i0] += delta;
+                s_minvD -= delta;
+                if (s_isD) s_done = 1;
+                else {
+                    used[s_j1] = 1;
+                    s_j0 = s_j1;
+                    if (p[s_j1] < 0) s_done = 2;
+                }
+            }
+            __syncthreads();
+            if (s_done) break;
+        }
+        if (tid == 0) {
+            // augment: shift the assignments back along the path; a path that ends in a dummy leaves its last row unmatched
+            int j = (s_done == 1) ? s_wayD : s_j0;
+            while (j >= 0) {
+                const int jp = way[j];
+                p[j] = (jp < 0) ? i0 : p[jp];
+                j = jp;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < m; i += blockDim.x) match_det[i] = -1;
+    __syncthreads();
+    for (int t = tid; t < T; t += blockDim.x) {
+        match_track[t] = p[t];
+        if (p[t] >= 0) match_det[p[t]] = t;
+    }
+}
+
 }  // namespace deft
 
 using namespace deft;
@@ -520,6 +653,30 @@ int deft_count_above(const float* scores, int K, float thresh, int* out, deft_st
     DEFT_REQUIRE(scores && out && K >= 1, "count_above: bad args");
     launch_pdl(count_above_kernel, dim3(1), dim3(256), 0, to_stream(s), scores, K, thresh, out);
     DEFT_CHECK_LAUNCH("count_above");
+    return DEFT_OK;
+}
+
+size_t deft_assign_workspace_bytes(int T, int m) { return align_up((size_t)m * ((T + 3) / 4 * 4) * sizeof(double), 256); }
+
+int deft_fuse_and_assign(const float* cost, int ldc, int T, int m, const int* m_dev, const float* pred_xy, const int* n_obs, const float* det_xy,
+                         double lambda, double cost_limit, int* match_track, int* match_det, void* ws, size_t ws_bytes, deft_stream_t s) {
+    DEFT_REQUIRE(cost && match_track && match_det && ws && T >= 1 && T <= 4096 && m >= 1 && m <= 1024 && ldc >= m, "fuse_and_assign: need 1<=T<=4096, 1<=m<=1024");
+    DEFT_REQUIRE((pred_xy == nullptr) == (n_obs == nullptr) && (pred_xy == nullptr) == (det_xy == nullptr), "fuse_and_assign: motion inputs come together");
+    if (ws_bytes < deft_assign_workspace_bytes(T, m)) { set_error("fuse_and_assign: workspace too small"); return DEFT_EWORKSPACE; }
+    const int ldT = (T + 3) / 4 * 4;
+    double* cs = reinterpret_cast<double*>(ws);
+    cudaStream_t st = to_stream(s);
+    const double gate = 5.0 * 5.9915;                     // 5 * chi2inv95[2] (kalman_filter.py:13-15, matching.py:326,343)
+    int blocks = ceil_div(T * m, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    launch_pdl(fuse_motion_kernel, dim3(blocks), dim3(256), 0, st, cost, ldc, T, m, m_dev, pred_xy, n_obs, det_xy, lambda, gate, 300, cost_limit, cs, ldT);
+    DEFT_CHECK_LAUNCH("fuse_motion");
+    const size_t smem = (size_t)T * (8 + 8 + 4 + 4 + 1) + (size_t)m * 8 + 64;
+    static size_t granted[DEFT_MAX_DEVICES] = {};
+    int rc = ensure_dyn_smem(assign_kernel, smem, granted, "assign_kernel");
+    if (rc != DEFT_OK) return rc;
+    launch_pdl(assign_kernel, dim3(1), dim3(1024), smem, st, (const double*)cs, ldT, T, m, m_dev, match_track, match_det);
+    DEFT_CHECK_LAUNCH("assign");
     return DEFT_OK;
 }
 

@@ -280,19 +280,20 @@ constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across pro
 // (tests/test_gpu_frame.py::test_c2_full_size_properties caught exactly that).
 constexpr int TS_ISSUERS = 2;
 #ifndef DEFT_TS_PAIR32
-#define DEFT_TS_PAIR32 1     // 1 = the N = 32 instantiation issues [hi|lo] as one N = 64 MMA (see TsCfg::PAIR)
+#define DEFT_TS_PAIR32 0     // 1 = the N = 32 instantiation issues [hi|lo] as one N = 64 MMA (see TsCfg::PAIR); measured neutral in r2 (producer-bound), off
 #endif
 #ifndef DEFT_TS_ISS128
-#define DEFT_TS_ISS128 1      // issuer warps of the N = 128 instantiations (A/B builds: make EXTRA=-DDEFT_TS_ISS128=2 OUT=...)
+#define DEFT_TS_ISS128 2      // issuer warps of the N = 128 instantiations (A/B builds: make EXTRA=-DDEFT_TS_ISS128=1 OUT=...)
 #endif
 
 template <int BN, int NPASS>
 struct TsCfg {
     static constexpr int ACOLS = NPASS == 3 ? 64 : 32;                 // TMEM columns of one A stage (hi [+ lo])
-    // Issuer warps.  N <= 64: two, alternating k-blocks (a 128x64x8 MMA executes in ~32 cycles but costs ~46 to issue, so
-    // one issuer leaves the pipe idle).  N = 128: ONE -- r2 trace (profiles/r2_tc_trace.md): the pipe already runs at
-    // its floor (766 cycles per k-block vs 12 x 64), what is lost is the epilogue, which with two private 128-column
-    // accumulators cannot be double-buffered; one issuer = one accumulator per tile = two sets in 256 columns.
+    // Issuer warps: two, alternating k-blocks (a 128x64x8 MMA executes in ~32 cycles but costs ~46 to issue, and an
+    // issuer also pays its own barrier waits and commits serially).  r2 tried ONE issuer for N = 128 so that the two
+    // accumulator sets fit twice in TMEM (double-buffered epilogue): the pipe, at its floor with two issuers (766 cycles
+    // per k-block = 12 x 64), fell to 1351 cycles per k-block -- 43.0 vs 35.8 us on the 128->128 3x3 layer
+    // (profiles/r2_engine_experiments.md).  DEFT_TS_ISS128 keeps the variant buildable.
     static constexpr int ISS = BN >= 128 ? DEFT_TS_ISS128 : TS_ISSUERS;
     // N = 32 (the DCN offset/mask convs), 3xTF32: a TS-mode MMA costs ~the same to issue at N = 32 as at N = 64, so the
     // two products that share A_hi are issued as ONE N = 64 instruction against the stage's [B_hi ; B_lo] rows (they

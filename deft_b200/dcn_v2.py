@@ -12,6 +12,29 @@ from torch import nn
 from . import _lib, ops, packing
 
 
+class _DCNFunction(torch.autograd.Function):
+    """The DCN module under autograd (training, BASELINE config C5): forward = deft_dcnv2_forward (fp32 SIMT engine: exact
+    arithmetic for gradient parity), backward = deft_dcnv2_backward (upstream dcn_v2_backward + the offset conv's backward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, om_weight, om_bias):
+        sd = {"d.weight": weight.detach(), "d.bias": bias.detach(), "d.conv_offset_mask.weight": om_weight.detach(),
+              "d.conv_offset_mask.bias": om_bias.detach()}
+        pk = packing.pack_dcn(sd, "d")
+        a = ops.as_nhwc(x.detach())
+        y = ops.dcnv2_forward(a, pk, relu=False, flags=0)
+        ctx.pk, ctx.a = pk, a
+        return y.nchw_view()
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        pk, a = ctx.pk, ctx.a
+        cin, cout = pk["cin"], pk["cout"]
+        gx, gw, gb, gwo, gbo = ops.dcnv2_backward(a, pk, ops.as_nhwc(grad_y.contiguous()))
+        unpack = lambda g, co: g[:, :co].reshape(3, 3, cin, co).permute(3, 2, 0, 1).contiguous()      # [(ky,kx,ci)][co] -> [co,ci,ky,kx]
+        return gx.nchw_view(), unpack(gw, cout), gb, unpack(gwo, 27), gbo[:27].contiguous()
+
+
 class DCN(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1):
         super().__init__()
@@ -47,6 +70,10 @@ class DCN(nn.Module):
 
     def forward(self, x, flags=0):
         _lib.require_device(x)
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            if self.out_channels % 16 != 0:
+                raise NotImplementedError("deft_b200.DCN backward needs out_channels % 16 == 0")
+            return _DCNFunction.apply(x, self.weight, self.bias, self.conv_offset_mask.weight, self.conv_offset_mask.bias)
         a = ops.as_nhwc(x)
         y = ops.dcnv2_forward(a, self.packed(), relu=False, flags=flags)
         return y.nchw_view()

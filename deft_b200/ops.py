@@ -438,3 +438,39 @@ def preprocess_warp(img_u8, inv_affine, mean, std, H, W, out=None):
     check(lib().deft_preprocess_warp(img_u8.data_ptr(), sh, sw, _lib.float_array(inv_affine), _lib.float_array(mean), _lib.float_array(std),
                                      out.data_ptr(), H, W, stream_ptr()), "preprocess_warp")
     return out
+
+
+@_on_input_device
+def dcnv2_backward(a: NHWC, pk, grad_y: NHWC):
+    """Backward of the bare DCN module (no BN).  a: input NHWC, grad_y: NHWC [N,H,W,Cout] -> (grad_x NHWC, grad_w [9Cin][ldw],
+    grad_b [Cout], grad_w_om [9Cin][32], grad_b_om [32]) in the forward's packed layouts."""
+    dev = a.t.device
+    cin, cout, ldw = pk["cin"], pk["cout"], pk["ldw"]
+    gx = NHWC.empty(a.N, a.H, a.W, cin, dev)
+    gw = torch.empty((9 * cin, ldw), dtype=torch.float32, device=dev)
+    gb = torch.empty(cout, dtype=torch.float32, device=dev)
+    gwo = torch.empty((9 * cin, 32), dtype=torch.float32, device=dev)
+    gbo = torch.empty(32, dtype=torch.float32, device=dev)
+    ws = torch.empty(lib().deft_dcnv2_backward_workspace_bytes(a.N, a.H, a.W, cin, cout), dtype=torch.uint8, device=dev)
+    check(lib().deft_dcnv2_backward(a.ptr, a.pitch, a.N, a.H, a.W, cin, pk["w_om"].data_ptr(), pk["b_om"].data_ptr(), pk["w"].data_ptr(), ldw, cout,
+                                    grad_y.ptr, grad_y.pitch, gx.ptr, gx.pitch, gwo.data_ptr(), gbo.data_ptr(), gw.data_ptr(), gb.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), stream_ptr()), "dcnv2_backward")
+    return gx, gw, gb, gwo, gbo
+
+
+@_on_input_device
+def fuse_and_assign(cost, m, cost_limit, lambda_=0.9, pred_xy=None, n_obs=None, det_xy=None, m_dev=None, match_track=None, match_det=None, ws=None):
+    """cost [T, ldc>=m] fp32 device -> (match_track int32 [T], match_det int32 [m]); the reference's fuse_motion (LSTM
+    branch) + linear_assignment(thresh=cost_limit), exact."""
+    T, ldc = cost.shape
+    dev = cost.device
+    if match_track is None:
+        match_track = torch.empty(T, dtype=torch.int32, device=dev)
+    if match_det is None:
+        match_det = torch.empty(m, dtype=torch.int32, device=dev)
+    if ws is None:
+        ws = torch.empty(lib().deft_assign_workspace_bytes(T, m), dtype=torch.uint8, device=dev)
+    check(lib().deft_fuse_and_assign(cost.data_ptr(), ldc, T, m, _p(m_dev), _p(pred_xy), _p(n_obs), _p(det_xy), C.c_double(lambda_),
+                                     C.c_double(cost_limit), match_track.data_ptr(), match_det.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),
+          "fuse_and_assign")
+    return match_track, match_det

@@ -44,7 +44,7 @@ class FramePipeline:
     uint8_norm (mean[3], std[3]): frames are uint8 HWC [1,H,W,3] and are normalised inside the stem (row f2)."""
 
     def __init__(self, model, opt, height, width, mem_frames=5, lstm=None, lstm_tracks=0, device=None, use_cuda_graph=True, depth=3,
-                 dense_streams=None, mem_rows=None, tracks=0, uint8_norm=None, score_thresh=None):
+                 dense_streams=None, mem_rows=None, tracks=0, uint8_norm=None, score_thresh=None, assign_thresh=None):
         self.model, self.opt = model, opt
         self.device = device or next(model.parameters()).device
         self.H, self.W = height, width
@@ -62,6 +62,9 @@ class FramePipeline:
         self.rows = min(self.P, self.K if mem_rows is None else mem_rows)
         self.T_tracks = tracks
         self.score_thresh = score_thresh
+        self.assign_thresh = assign_thresh          # row f3: linear_assignment(cost, thresh) on the device + node append (tracker.py:915)
+        if assign_thresh is not None and not tracks:
+            raise ValueError("assign_thresh needs tracks > 0 (the assignment consumes the [tracks, dets] cost matrix)")
         self.uint8_norm = uint8_norm
         self.use_cuda_graph = use_cuda_graph
         self.cemb = sum(model.AFE.selector_output_channel)
@@ -93,6 +96,10 @@ class FramePipeline:
                 self.node_cnt = torch.zeros(tracks, dtype=torch.int32, device=dev)
                 self.sim = [torch.zeros((tracks, P + 1), dtype=torch.float32, device=dev) for _ in range(depth)]
                 self.cost = [torch.zeros((tracks, P), dtype=torch.float32, device=dev) for _ in range(depth)]
+                if assign_thresh is not None:
+                    self.match_track = [torch.full((tracks,), -1, dtype=torch.int32, device=dev) for _ in range(depth)]
+                    self.match_det = [torch.full((self.K,), -1, dtype=torch.int32, device=dev) for _ in range(depth)]
+                    self.assign_ws = torch.empty(_lib.lib().deft_assign_workspace_bytes(tracks, self.K), dtype=torch.uint8, device=dev)
             if lstm is not None:
                 fin = lstm.model.fin
                 self.lstm_h = torch.zeros((self.T, 128), device=dev)
@@ -188,6 +195,14 @@ class FramePipeline:
                                  self.mm, self.m_frame, self.sim[slot], self.cost[slot], m_dev=self.m_dev)
             res["similarity"] = self.sim[slot]
             res["cost"] = self.cost[slot]
+            if self.assign_thresh is not None:
+                # association on the device: appearance cost -> exact linear assignment -> the matched tracks get this frame's node
+                # (motion fusion is available through ops.fuse_and_assign for callers that keep the tracks' predictions on the device)
+                ops.fuse_and_assign(self.cost[slot], self.K, self.assign_thresh, m_dev=self.m_dev, match_track=self.match_track[slot],
+                                    match_det=self.match_det[slot], ws=self.assign_ws)
+                ops.track_append(self.match_track[slot], self.clock, self.node_frame, self.node_id, self.node_cnt)
+                res["match_track"] = self.match_track[slot]
+                res["match_det"] = self.match_det[slot]
         if self.lstm is not None:
             hn, cn, pred = self.lstm.predict_batch(self.lstm_h, self.lstm_c, self.lstm_x)
             self.lstm_h.copy_(hn)
@@ -208,7 +223,10 @@ class FramePipeline:
         dense plan (111 launches) and the tail.  The recorder state is restored afterwards: warm-up frames are not part
         of the stream."""
         with _lib.on_device(self.device):
-            state = [t.clone() for t in (self.memory, self.au_mem, self.clock, self.slot_frame, self.counts)]
+            saved = [self.memory, self.au_mem, self.clock, self.slot_frame, self.counts]
+            if self.T_tracks:
+                saved += [self.node_frame, self.node_id, self.node_cnt]
+            state = [t.clone() for t in saved]
             lstm_state = [self.lstm_h.clone(), self.lstm_c.clone()] if self.lstm is not None else None
             res = None
             for slot in range(self.depth):
@@ -233,7 +251,7 @@ class FramePipeline:
                             self.out[slot] = self._tail(slot)
                         self.tail_graph[slot] = g
                 torch.cuda.synchronize(self.device)
-            for t, s in zip((self.memory, self.au_mem, self.clock, self.slot_frame, self.counts), state):
+            for t, s in zip(saved, state):
                 t.copy_(s)
             if lstm_state is not None:
                 self.lstm_h.copy_(lstm_state[0]); self.lstm_c.copy_(lstm_state[1])
@@ -295,6 +313,8 @@ class FramePipeline:
     def host_keys(self):
         """What step() brings back to the host: the detections and ONE matrix -- the [tracks, dets] cost when the
         track reduction is on (row f1), otherwise the raw per-memory-frame affinity block the reference copies."""
+        if self.T_tracks and self.assign_thresh is not None:
+            return ("scores", "clses", "bboxes", "match_det")          # association done on the device: only the matches travel
         return ("scores", "clses", "bboxes", "cost") if self.T_tracks else ("scores", "clses", "bboxes", "affinity")
 
     def step(self, image_host, out_host=None):
@@ -335,13 +355,14 @@ class FramePipeline:
         (deft_launch_count); one eager frame is run between two readings (recorder state restored)."""
         with _lib.on_device(self.device):
             torch.cuda.synchronize(self.device)
-            state = [t.clone() for t in (self.memory, self.au_mem, self.clock, self.slot_frame, self.counts)]
+            saved = [self.memory, self.au_mem, self.clock, self.slot_frame, self.counts] + ([self.node_frame, self.node_id, self.node_cnt] if self.T_tracks else [])
+            state = [t.clone() for t in saved]
             before = _lib.lib().deft_launch_count()
             self.plans[0].launch()
             self._tail(0)
             torch.cuda.synchronize(self.device)
             n = int(_lib.lib().deft_launch_count() - before)
-            for t, s in zip((self.memory, self.au_mem, self.clock, self.slot_frame, self.counts), state):
+            for t, s in zip(saved, state):
                 t.copy_(s)
             torch.cuda.synchronize(self.device)
             return n

@@ -234,6 +234,18 @@ int deft_track_similarity(const float* aff, int F, int P, const int* clock, cons
 int deft_track_append(const int* match, const int* clock, int T, int* node_frame, int* node_id, int* node_cnt, deft_stream_t s);
 int deft_count_above(const float* scores, int K, float thresh, int* out, deft_stream_t s);
 
+/* ---- f3: motion fusion + linear assignment on the device (matching.py:40-55, 311-364; tracker.py:886-915).
+ * cost [T, ldc] fp32 (= 1 - similarity, row per track), m live detections (or *m_dev).  Motion inputs (all or none):
+ * pred_xy [T,2] the tracks' predicted centres for this frame, n_obs [T] observation counts, det_xy [m,2] detection
+ * centres: the reference's LSTM branch of fuse_motion (>= 300 observations: gate at 5*chi2inv95[2] on the squared
+ * centre distance, cost = lambda*cost + 0.05*(1-lambda)*d2; younger tracks: lambda*cost, the reference's empty-slice
+ * "gaussian" metric).  Assignment = lap.lapjv(cost, extend_cost=True, cost_limit) solved exactly in fp64 (shortest
+ * augmenting paths): match_track[T] = detection or -1, match_det[m] = track or -1.  ws >= deft_assign_workspace_bytes. */
+size_t deft_assign_workspace_bytes(int T, int m);
+int deft_fuse_and_assign(const float* cost, int ldc, int T, int m, const int* m_dev, const float* pred_xy, const int* n_obs,
+                         const float* det_xy, double lambda_, double cost_limit, int* match_track, int* match_det, void* ws,
+                         size_t ws_bytes, deft_stream_t s);
+
 /* ---- f2: pre-processing (detector.py:377-422).  deft_stem_conv7x7_u8 = deft_stem_conv7x7 reading a uint8 HWC frame
  * [N,H,W,3] already at network resolution, normalisation (u8/255 - mean[c])/std[c] fused into the load (x_nchw: optional
  * fp32 NCHW copy of the normalised frame, NULL = none).  deft_preprocess_warp: general inverse-affine bilinear warp +
@@ -243,6 +255,16 @@ int deft_stem_conv7x7_u8(const unsigned char* img, int N, int H, int W, const fl
                          float* x_nchw, deft_stream_t s);
 int deft_preprocess_warp(const unsigned char* img, int src_h, int src_w, const float* inv_affine_host, const float* mean_host,
                          const float* std_host, float* out_nchw, int H, int W, deft_stream_t s);
+
+/* ---- f4 (training, BASELINE config C5): backward of the DCN module (upstream dcn_v2_backward + the offset/mask conv's own
+ * backward), fp32.  Inputs as deft_dcnv2_forward (no BN: the bare module, bias included) plus grad_y [N*H*W, gy_pitch].
+ * Outputs: grad_x [N*H*W, gx_pitch] (written), grad_w [9*Cin][ldw] and grad_w_om [9*Cin][32] in the packed layout of
+ * the forward weights, grad_b [Cout], grad_b_om [32] (entries >= 27 are 0).  Needs Cout % 16 == 0 (ldw == Cout).
+ * grad_x's deformable part is accumulated with float atomics (as upstream's col2im): run-to-run bit differences. */
+size_t deft_dcnv2_backward_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int deft_dcnv2_backward(const float* x, int x_pitch, int N, int H, int W, int Cin, const float* w_om_packed, const float* b_om,
+                        const float* w_packed, int ldw, int Cout, const float* grad_y, int gy_pitch, float* grad_x, int gx_pitch,
+                        float* grad_w_om, float* grad_b_om, float* grad_w, float* grad_b, void* ws, size_t ws_bytes, deft_stream_t s);
 
 /* ---- a10: KalmanFilterLSTM.predict (kalman_filter_lstm.py:65-78) for T independent tracks in one
  * launch: one LSTM step (gate order i,f,g,o) + out1 (128->64, no activation) + out2 (64->nout).

@@ -439,3 +439,54 @@ def warp_affine_bilinear(img_u8_hwc, inv_affine, H, W):
     top = at(y0, x0) + lx[..., None] * (at(y0, x0 + 1) - at(y0, x0))
     bot = at(y0 + 1, x0) + lx[..., None] * (at(y0 + 1, x0 + 1) - at(y0 + 1, x0))
     return top + ly[..., None] * (bot - top)
+
+
+# --------------------------------------------------------------------------- f3: motion fusion + linear assignment
+CHI2INV95_2 = 5.9915                                         # kalman_filter.py:13-15 (chi2inv95[2])
+
+
+def fuse_motion_lstm(cost, pred_xy, n_obs, det_xy, lambda_=0.9):
+    """matching.fuse_motion (matching.py:311-364), use_lstm=True, only_position=True, covariance = eye (tracker.py:200).
+    cost [T,m] float64; pred_xy [T,2] = track.prediction_at_frame(frame_id)[:2]; n_obs [T] = len(track.observations).
+    >= 300 observations: metric "maha" = squared centre distance (kalman_filter_lstm.py:95-101 with identity covariance);
+    fewer: metric "gaussian", whose d = measurements[:, 3:-1] - mean[3:-1] is EMPTY for 2-vectors (lines 91-94), i.e. 0."""
+    cost = np.array(cost, dtype=np.float64, copy=True)
+    if cost.size == 0:
+        return cost
+    gating_threshold = CHI2INV95_2
+    for row in range(cost.shape[0]):
+        if n_obs[row] >= 300:
+            d = np.asarray(det_xy, dtype=np.float64) - np.asarray(pred_xy[row], dtype=np.float64)
+            gd = np.sum(d * d, axis=1)
+            cost[row, gd > 5.0 * gating_threshold] = np.inf
+            cost[row] = lambda_ * cost[row] + 0.05 * (1 - lambda_) * gd
+        else:
+            gd = np.zeros(cost.shape[1])
+            cost[row, gd > 50] = np.inf
+            cost[row] = lambda_ * cost[row] + 0.0005 * (1 - lambda_) * gd
+    return cost
+
+
+def linear_assignment(cost, thresh):
+    """matching.linear_assignment (matching.py:40-55) = lap.lapjv(cost, extend_cost=True, cost_limit=thresh).  `lap`
+    (requirements.txt:14, unpinned, absent here) extends the matrix to (n+m)^2 with cost_limit/2 off the real block and 0 in
+    the dummy-dummy block (lap/_lapjv.pyx: `cost_c_extended[:] = cost_limit / 2.`), solves the square problem and
+    reports x[i] = -1 for rows matched to a dummy.  Restated with scipy's exact solver on the same extended matrix.
+    Returns (x [n] column of row i or -1, y [m] row of column j or -1)."""
+    from scipy.optimize import linear_sum_assignment
+    cost = np.asarray(cost, dtype=np.float64)
+    n, m = cost.shape
+    if cost.size == 0:
+        return -np.ones(n, dtype=np.int64), -np.ones(m, dtype=np.int64)
+    ext = np.full((n + m, n + m), thresh / 2.0)
+    ext[n:, m:] = 0.0
+    ext[:n, :m] = cost
+    big = 1e9                                                # scipy rejects rows that are entirely inf; gated pairs can never win anyway
+    r, c = linear_sum_assignment(np.where(np.isfinite(ext), ext, big))
+    x = -np.ones(n, dtype=np.int64)
+    y = -np.ones(m, dtype=np.int64)
+    for i, j in zip(r, c):
+        if i < n and j < m and np.isfinite(cost[i, j]):
+            x[i] = j
+            y[j] = i
+    return x, y

@@ -190,3 +190,29 @@ def test_preprocess_restatement_vs_cv2():
     x = restate.normalize_u8(src, [0.408, 0.447, 0.470], [0.289, 0.274, 0.278])
     assert x.shape == (1, 3, 70, 110) and x.dtype == torch.float32
     assert abs(float(x[0, 1, 3, 4]) - ((src[3, 4, 1] / 255.0 - 0.447) / 0.274)) < 1e-6
+
+
+def test_linear_assignment_restatement_is_optimal_on_small_cases():
+    """Row f3 oracle: the restated lapjv(extend_cost, cost_limit) equals the brute-force optimum of
+    sum(matched c) + limit/2 * (#unmatched rows + #unmatched cols) on every small matrix tried."""
+    import itertools
+    rng = np.random.RandomState(3)
+    for n, m in ((3, 3), (4, 2), (2, 5), (5, 4)):
+        for _ in range(6):
+            cost = rng.rand(n, m)
+            thresh = 0.6
+            x, y = restate.linear_assignment(cost, thresh)
+            best, arg = None, None
+            cols = list(range(m)) + [-1] * n
+            for perm in set(itertools.permutations(cols, n)):
+                used = [j for j in perm if j >= 0]
+                if len(set(used)) != len(used):
+                    continue
+                k = len(used)
+                tot = sum(cost[i, j] for i, j in enumerate(perm) if j >= 0) + thresh / 2 * ((n - k) + (m - k))
+                if best is None or tot < best - 1e-12:
+                    best, arg = tot, perm
+            assert list(x) == list(arg), (cost, x, arg)
+            assert all(cost[i, j] <= thresh for i, j in enumerate(x) if j >= 0)
+    fused = restate.fuse_motion_lstm(np.array([[0.5, 0.2], [0.3, 0.4]]), np.array([[0., 0.], [10., 10.]]), [300, 5], np.array([[1., 1.], [9., 9.]]))
+    assert np.isinf(fused[0, 1]) and abs(fused[0, 0] - (0.45 + 0.005 * 2.0)) < 1e-12 and np.allclose(fused[1], [0.27, 0.36])

@@ -47,3 +47,55 @@ def test_two_rank_gloo_aggregation():
 def test_single_process_passthrough():
     fps, ms = aggregate_throughput(30.0, 500.0)
     assert fps == 60.0 and ms == 500.0
+
+
+def _ddp_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deft_b200.train import BucketedGradAllReduce
+    torch.manual_seed(0)                                        # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 3))
+    unused = torch.nn.Parameter(torch.ones(5))                  # a parameter no loss touches: still reduced (as zeros)
+    red = BucketedGradAllReduce(list(net.parameters()) + [unused], bucket_bytes=6000)
+    assert len(red.buckets) >= 3
+    g = torch.Generator(); g.manual_seed(100 + rank)            # different data per rank
+    x = torch.randn(8, 16, generator=g)
+    net(x).square().mean().backward()
+    red.finish()
+    q.put((rank, [p.grad.clone() for p in net.parameters()], unused.grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_grad_allreduce_world2_gloo():
+    """Config C5's collective: the bucketed, hook-driven gradient all-reduce equals the average of the per-rank gradients
+    (world_size 2, gloo on CPU; the same class runs over NCCL on the GPUs)."""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29671
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # reference: the two local gradients averaged
+    grads = []
+    for rank in range(2):
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 3))
+        g = torch.Generator(); g.manual_seed(100 + rank)
+        net(torch.randn(8, 16, generator=g)).square().mean().backward()
+        grads.append([p.grad.clone() for p in net.parameters()])
+    want = [(a + b) / 2 for a, b in zip(*grads)]
+    for rank in range(2):
+        for got, w in zip(res[rank][1], want):
+            assert torch.allclose(got, w, rtol=1e-6, atol=1e-7)
+        assert float(res[rank][2].abs().max()) == 0.0

@@ -7,7 +7,7 @@ import torch
 from deft_b200 import ops, packing
 from oracle import spec
 
-CASES = {"conv64": ("conv", 64, 64, 3, 152, 272), "conv128": ("conv", 128, 128, 3, 76, 136), "conv1x1": ("conv", 128, 64, 1, 152, 272),
+CASES = {"conv32": ("conv", 64, 32, 3, 152, 272), "conv64": ("conv", 64, 64, 3, 152, 272), "conv128": ("conv", 128, 128, 3, 76, 136), "conv1x1": ("conv", 128, 64, 1, 152, 272),
          "dcn64": ("dcn", 64, 64, 3, 152, 272), "dcn128": ("dcn", 128, 128, 3, 76, 136)}
 case = sys.argv[1] if len(sys.argv) > 1 else "conv64"
 kind, cin, cout, k, H, W = CASES[case]
