@@ -65,7 +65,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a protocol bug must trap, never hang the GPU.  After ~0.5 s every stuck warp reports where it waits
 // (site / aux are caller-defined: which barrier of the protocol, which k-block or tile), after ~1.5 s the kernel traps.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int aux = 0) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int aux = 0, volatile int* prog = nullptr, int slot = 0) {
+    // prog (TS kernel): a per-CTA progress board in shared memory -- every role's leader posts (site << 24 | counter) before it
+    // waits, so that a stall report shows where ALL roles of the CTA stand, not only the warp that timed out
+    if (prog != nullptr && (threadIdx.x & 31) == 0) prog[slot] = (site << 24) | (aux & 0xffffff);
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     bool reported = false;
@@ -73,8 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int sit
         const long long dt = clock64() - t0;
         if (dt > 1000000000LL && !reported) {
             reported = true;
-            if ((threadIdx.x & 31) == 0)
+            if ((threadIdx.x & 31) == 0) {
                 printf("deft tc_engine: mbarrier stall block %d warp %d site %d aux %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, site, aux, bar, parity);
+                if (prog != nullptr)
+                    printf("deft tc_engine: block %d roles (site<<24|count): prod %x %x %x %x | issuer %x %x | bcopy %x | epi %x | tma %x\n", blockIdx.x,
+                           prog[0], prog[1], prog[2], prog[3], prog[4], prog[5], prog[6], prog[7], prog[8]);
+            }
         }
         if (dt > 3000000000LL) __trap();
     }

@@ -425,6 +425,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     auto p_full = [&](int s) { return bar_base + 8u * (40 + s); };
     auto p_empty = [&](int s) { return bar_base + 8u * (44 + s); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
+    // progress board for stall reports (static shared memory: its address costs no register): see mbar_wait
+    __shared__ int prog_board[16];
+    volatile int* const prog = prog_board;
     unsigned char* epi_stage = smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 512;     // epilogue warps' transpose stages, scale, shift
     unsigned char* ap_common = epi_stage + TS_EPI_SMEM;                                  // producer warps' transpose stages + row tables
     unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
@@ -445,6 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             mbar_init(p_full(s), 1);
             mbar_init(p_empty(s), TC_PWARPS);
         }
+        for (int q = 0; q < 16; ++q) prog[q] = 0;
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                             if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
                         }
                         const int gc = gc0 + c;
-                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc);
+                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
                         pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * TP_STAGE_BYTES);
                         last_c = c;
                     }
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                         for (int q = 0; q < 8; ++q) x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (tid == grp * 128) TC_TRACE(1, gk, 1);
-                    mbar_wait(a_empty(sa), pa ^ 1u, 2, gk);
+                    mbar_wait(a_empty(sa), pa ^ 1u, 2, gk, quad == 0 ? prog : nullptr, grp);
                     __syncwarp();                              // converged before the .aligned tcgen05.st
                     tc_fence_after();
                     if (tid == grp * 128) TC_TRACE(1, gk, 2);
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 if (!(dbg & 2)) ap.fill(kb0 + i, quad, lane, meta, stage);     // coalesced loads -> private smem stage
                 __syncwarp();
                 if (tid == grp * 128) TC_TRACE(1, gk, 1);
-                mbar_wait(a_empty(sa), pa ^ 1u, 2, gk);
+                mbar_wait(a_empty(sa), pa ^ 1u, 2, gk, quad == 0 ? prog : nullptr, grp);
                     __syncwarp();                              // converged before the .aligned tcgen05.st
                 tc_fence_after();
                 if (tid == grp * 128) TC_TRACE(1, gk, 2);
@@ -610,7 +614,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const int kb0 = z * ts.kb_per_split;
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 0);
-            mbar_wait(acc_full(b), (uint32_t)(iter / Cfg::NBUF) & 1u, 3, iter);
+            mbar_wait(acc_full(b), (uint32_t)(iter / Cfg::NBUF) & 1u, 3, iter, ewarp == 0 ? prog : nullptr, 7);
             __syncwarp();                                  // converged before the .aligned tcgen05.ld
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
             const int b = iter % Cfg::NBUF;
             const uint32_t tile_par = (uint32_t)(iter / Cfg::NBUF) & 1u;
-            mbar_wait(acc_empty(b), tile_par ^ 1u, 4, iter);
+            mbar_wait(acc_empty(b), tile_par ^ 1u, 4, iter, prog, 4 + w);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)((b * Cfg::ISS + w) * Cfg::ACCW);
             for (int i = w; i < nkb; i += Cfg::ISS) {
@@ -657,9 +661,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int s_b = gk % sb;
                 const uint32_t ph_b = (uint32_t)(gk / sb) & 1u;
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 0);
-                mbar_wait(a_full(sa), pa, 5, gk);
+                mbar_wait(a_full(sa), pa, 5, gk, prog, 4 + w);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 1);
-                mbar_wait(b_full(s_b), ph_b, 6, gk);
+                mbar_wait(b_full(s_b), ph_b, 6, gk, prog, 4 + w);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 2);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
@@ -707,7 +711,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const unsigned char* src = reinterpret_cast<const unsigned char*>(wblob) + ((size_t)ntile * ts.nkb_total + kb0) * (2 * Cfg::B_TILE);
             for (int i = 0; i < nkb; ++i, ++gk) {
                 if (lane == 0) TC_TRACE(2, gk, 0);
-                mbar_wait(b_empty(s_b), ph_b ^ 1u, 7, gk);
+                mbar_wait(b_empty(s_b), ph_b ^ 1u, 7, gk, prog, 6);
                 if (lane == 0) TC_TRACE(2, gk, 1);
                 const uint32_t dst = sbase + (uint32_t)s_b * Cfg::B_STAGE;
                 if (elect_one_sync()) {
@@ -737,7 +741,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int c0 = kb0 / 9, nch = nkb / 9;
                 for (int c = 0; c < nch; ++c, ++gc) {
                     const int s = gc % ps;
-                    mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc);
+                    mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc, prog, 8);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
                         tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
@@ -746,6 +750,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 }
             }
         }
+    }
+    if (lane == 0) {                                       // role finished its tile loop (shows as site 0xee on the progress board)
+        const int slot = warp < TC_PWARPS ? ((warp & 3) == 0 ? (warp >> 2) : -1) : warp < TC_MMA_WARP ? (warp == TC_PWARPS ? 7 : -1)
+                         : warp < TC_AUX_WARP ? 4 + (warp - TC_MMA_WARP) : warp == TC_AUX_WARP ? 6 : 8;
+        if (slot >= 0) prog[slot] = 0xee << 24;
     }
     __syncthreads();
     if (warp == TC_AUX_WARP) {
