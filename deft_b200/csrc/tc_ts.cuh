@@ -327,7 +327,7 @@ struct TsRowMap {                                                   // accumulat
     }
 };
 template <int BN>
-__device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc, int nblk, int ewarp, int lane, const TsRowMap& rm, int ntile,
+__device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc, int nblk, float gain, int ewarp, int lane, const TsRowMap& rm, int ntile,
                                             int z, float* stage, const float* ss) {   // nblk consecutive BN-wide partial accumulators are added in order
     const Epilogue& e = epi.e;
     constexpr int LW = BN >= 32 ? 32 : BN;
@@ -352,7 +352,8 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
             }
 #pragma unroll
             for (int q = 0; q < LH / 4; ++q)
-                *reinterpret_cast<float4*>(stage + lane * TS_EPI_LD + h + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                *reinterpret_cast<float4*>(stage + lane * TS_EPI_LD + h + q * 4) =
+                    make_float4(v[q * 4] * gain, v[q * 4 + 1] * gain, v[q * 4 + 2] * gain, v[q * 4 + 3] * gain);
         }
         __syncwarp();
         const int col = ntile * BN + c + cq;                        // this lane's 4 output channels
@@ -400,7 +401,7 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
 
 template <class AP, int BN, int NPASS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_constant__ AP ap_param, const float* __restrict__ wblob, TileSched ts,
-                                                              int M, int sb, int ps, EpiStd epi, int dbg, long long* trace) {
+                                                              int M, int sb, int ps, EpiStd epi, int dbg, long long* trace, float rz_comp) {
     using Cfg = TsCfg<BN, NPASS>;
     constexpr int SA = Cfg::SA;
     constexpr bool kPatch = AP::kPatch;
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");
         pdl_wait();                                       // residual reads, output / scratch writes
-        int iter = 0;
+        int iter = 0, gk0 = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
             const int m0 = (mn / ts.n_tiles) * TC_BM, ntile = mn % ts.n_tiles;
@@ -618,8 +619,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             __syncwarp();                                  // converged before the .aligned tcgen05.ld
             if (ewarp == 0 && lane == 0) TC_TRACE(3, iter, 1);
             tc_fence_after();
-            // issuer 1's accumulator holds a partial sum only when the tile has >= 2 k-blocks
+            // Issuer w owns the k-blocks whose GLOBAL index is congruent to w (see the issuer loop), so with a single k-block
+            // only the accumulator of issuer (gk0 % ISS) holds data; otherwise all of them do.
+            const int first_iss = (Cfg::ISS > 1 && nkb == 1) ? (gk0 % Cfg::ISS) : 0;
             const int nblk = ((Cfg::ISS > 1 && nkb > 1) ? Cfg::ISS : 1) * Cfg::NBLK;
+            // The tensor core adds every MMA into the fp32 accumulator with round-toward-zero (measured: tools/tc_bias.py, a
+            // gain of -1.6e-8 per accumulate step, e.g. -6.8e-6 at K = 2304).  An accumulator of this tile took
+            // 4 * NPASS * ceil(nkb / ISS) steps; the expected shrink is undone here (DEFT_TC_RZ_COMP=0 disables it).
+            const float rz_gain = 1.0f + rz_comp * (float)(4 * NPASS * ((nkb + Cfg::ISS - 1) / Cfg::ISS));
             TsRowMap rm{};
             rm.M = M;
             if constexpr (kPatch) {
@@ -631,8 +638,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 rm.base = m0;                              // W = 0: rows are consecutive pixels
             }
             if (!(dbg & 16))
-                ts_epilogue<BN>(epi, tmem_base + (uint32_t)(b * Cfg::ISS * Cfg::ACCW), nblk, ewarp, lane, rm, ntile, z,
+                ts_epilogue<BN>(epi, tmem_base + (uint32_t)((b * Cfg::ISS + first_iss) * Cfg::ACCW), nblk, rz_gain, ewarp, lane, rm, ntile, z,
                                 reinterpret_cast<float*>(epi_stage) + ewarp * 32 * TS_EPI_LD, ss);
+            gk0 += nkb;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(b));
@@ -654,7 +662,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             mbar_wait(acc_empty(b), tile_par ^ 1u, 4, iter, prog, 4 + w);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + (uint32_t)((b * Cfg::ISS + w) * Cfg::ACCW);
-            for (int i = w; i < nkb; i += Cfg::ISS) {
+            // Ownership by GLOBAL k-block index: issuer w takes gk with gk % ISS == w.  The A ring depth (4 or 6) and ISS (2) are
+            // both even, so a ring stage is then consumed by the same issuer for the whole kernel.  r1 split by the tile-local
+            // index; with an odd k-block count per tile (Cin = 32 3x3: 9) stage ownership flipped from tile to tile, an issuer
+            // could run two uses of a stage ahead of the other one, and its parity wait on a_full was then satisfied by the
+            // WRONG phase (stale operand, then a desynchronised ring: the C4 stall of round 2, the stream-K hang of round 1).
+            const int i_first = (w - (gk0 % Cfg::ISS) + Cfg::ISS) % Cfg::ISS;
+            for (int i = i_first; i < nkb; i += Cfg::ISS) {
                 const int gk = gk0 + i;
                 const int sa = gk % SA;
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
@@ -678,15 +692,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                         if constexpr (Cfg::PAIR) {
                             // A_hi x [B_hi ; B_lo] as one N = 2*BN MMA (initialises / accumulates both column blocks),
                             // then the A_lo x B_hi correction into the first block
-                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, make_idesc(2 * BN), (i > w || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, make_idesc(2 * BN), (i > i_first || k > 0) ? 1u : 0u);
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, 1u);
                         } else if (NPASS == 3) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);
-                            umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > w || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_lo, idesc, 1u);
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, 1u);
                         } else {
-                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, (i > w || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(a_empty(sa));
@@ -696,7 +710,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 __syncwarp();
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 3);
             }
-            if (w >= nkb && lane == 0) mbar_arrive(acc_full(b));    // no k-block for this issuer in the tile
+            if (i_first >= nkb && lane == 0) mbar_arrive(acc_full(b));    // no k-block for this issuer in the tile
             gk0 += nkb;
         }
     } else if (warp == TC_AUX_WARP) {
@@ -807,7 +821,9 @@ static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tile
     if (dbg < 0) { const char* e = getenv("DEFT_TC_DBG"); dbg = e ? atoi(e) : 0; }
     long long* trace = debug_trace_ptr();
     const int grid = ts.total < TC_NUM_SMS ? ts.total : TC_NUM_SMS;
-    if (launch_pdl(tc_ts_kernel<AP, BN, NPASS>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, sb, ps, epi, dbg, trace) != cudaSuccess) {
+    static float rz = -1.f;
+    if (rz < 0.f) { const char* e = getenv("DEFT_TC_RZ_COMP"); rz = (e && atoi(e) == 0) ? 0.f : 1.6e-8f; }
+    if (launch_pdl(tc_ts_kernel<AP, BN, NPASS>, dim3(grid), dim3(TC_THREADS), smem, st, ap, blob, ts, M, sb, ps, epi, dbg, trace, rz) != cudaSuccess) {
         set_error("tc_ts_kernel: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         return DEFT_ECUDA;
     }

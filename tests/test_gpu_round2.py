@@ -445,3 +445,37 @@ def test_pipeline_device_assignment_closes_the_loop(dev):
         for k in np.nonzero(x_ref >= 0)[0]:
             c = int(pipe.node_cnt[k])
             assert int(pipe.node_frame[k, c - 1]) == t and int(pipe.node_id[k, c - 1]) == x_ref[k]
+
+
+# ------------------------------------------------------------------------------------------------ engine protocol regression
+def test_odd_kblock_count_many_tiles_per_cta_is_stable(dev):
+    """Regression for the round-2 C4 stall: a layer with an ODD number of k-blocks per tile (3x3, 32 input channels: 9) and
+    five tiles per CTA (232x408 outputs = 740 tiles on 148 CTAs).  With tile-local k-block ownership the two MMA issuers
+    drifted apart and a parity wait matched the wrong mbarrier phase (stale operand / deadlock); ownership is now by the
+    global k-block index.  The layer must finish, agree with the fp32 SIMT engine and be bit-identical run to run."""
+    from deft_b200 import ops, packing
+    cin, cout, k, H, W = 32, 64, 3, 464, 816
+    w = (torch.rand(cout, cin, k, k, generator=torch.Generator().manual_seed(3)) * 2 - 1) * (3.0 / (cin * k * k)) ** 0.5
+    wp, ldw = packing.pack_conv(w.to(dev))
+    sc = (torch.rand(cout, generator=torch.Generator().manual_seed(4)) + 0.5).to(dev)
+    sh = torch.zeros(cout, device=dev)
+    x = ops.as_nhwc(spec.make_input((1, cin, H, W), tag="oddkb").to(dev))
+    ref = ops.conv2d_bn_act([x], wp, ldw, sc, sh, cout, k, k, 2, 1, True, flags=0).nchw_view().clone()
+    M = (H // 2) * (W // 2)
+    w_tc, bn = ops.tc_pack(wp, ldw, wp.shape[0], M, taps=k * k)
+    first = None
+    for it in range(25):
+        y = ops.conv2d_bn_act([x], wp, ldw, sc, sh, cout, k, k, 2, 1, True, flags=2, w_tc=w_tc, tc_bn=bn).nchw_view()
+        torch.cuda.synchronize()
+        if first is None:
+            first = y.clone()
+            assert nerr(first.cpu(), ref.cpu()) < 1e-5
+        else:
+            assert torch.equal(y, first), it
+    # single k-block per tile (1x1, 32 channels): only one issuer's accumulator holds data, alternating with the global index
+    w1 = (torch.rand(48, 32, 1, 1, generator=torch.Generator().manual_seed(5)) * 2 - 1) * 0.3
+    wp1, ldw1 = packing.pack_conv(w1.to(dev))
+    sc1, sh1 = torch.ones(48, device=dev), torch.zeros(48, device=dev)
+    r1 = ops.conv2d_bn_act([x], wp1, ldw1, sc1, sh1, 48, 1, 1, 1, 0, False, flags=0).nchw_view()
+    y1 = ops.conv2d_bn_act([x], wp1, ldw1, sc1, sh1, 48, 1, 1, 1, 0, False, flags=2).nchw_view()
+    assert nerr(y1.cpu(), r1.cpu()) < 1e-5
