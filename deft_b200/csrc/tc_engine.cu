@@ -23,6 +23,7 @@
 //   (profiles/r1_streamk_experiment.md).
 // * Every mbarrier wait is bounded (mbar_wait): a protocol bug reports its site and traps, it never hangs the GPU.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <type_traits>
 #include "tc_engine.cuh"
 #include <stdlib.h>
@@ -834,6 +835,44 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wp, int ldw, in
     }
 }
 
+// 3xFP16 weight images (TsCfg::F16): k-blocks of 64 channels, [n_tiles][nkb][hi|lo][BN rows x 128 B swizzled] of fp16,
+// w = hi + lo + O(2^-22 w).  perm_taps > 0: K order (64-channel block, tap, channel).
+__global__ void tc_pack_weights_f16_kernel(const float* __restrict__ wp, int ldw, int K, int BN, int nkb, int n_tiles, int perm_taps,
+                                           __half* __restrict__ blob) {
+    size_t total = (size_t)n_tiles * nkb * BN * 64;
+    const int ctot = perm_taps ? K / perm_taps : 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int kk = (int)(i % 64);
+        size_t t = i / 64;
+        int n = (int)(t % BN);
+        t /= BN;
+        int kb = (int)(t % nkb);
+        int nt = (int)(t / nkb);
+        int k = kb * 64 + kk, co = nt * BN + n;
+        if (perm_taps) {
+            int cb = kb / perm_taps, tap = kb - cb * perm_taps;
+            k = tap * ctot + cb * 64 + kk;
+        }
+        float w = (k < K && co < ldw) ? wp[(size_t)k * ldw + co] : 0.f;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        size_t tile = ((size_t)nt * nkb + kb) * (size_t)(2 * BN * 64);       // halves per (hi + lo) tile pair
+        size_t off = (size_t)n * 64 + (size_t)(((kk >> 3) ^ (n & 7)) << 3) + (kk & 7);
+        blob[tile + off] = hi;
+        blob[tile + (size_t)BN * 64 + off] = lo;
+    }
+}
+
+// Which numeric mode a weight image is packed for -- a pure function of (K, taps, bn) so that the packer and every dispatcher
+// agree without a flag travelling with the blob: 3xFP16 when enabled (DEFT_TC_F16, default off until measured), the tile is a TS-kernel
+// tile (bn <= 128) and the channel count per tap is a multiple of 64; else 3xTF32.
+bool tc_blob_is_f16(int K, int taps, int bn) {
+    static int en = -1;
+    if (en < 0) { const char* e = getenv("DEFT_TC_F16"); en = e ? atoi(e) : 0; }
+    if (taps < 1) taps = 1;
+    return en != 0 && bn <= 128 && K % taps == 0 && (K / taps) % 64 == 0;
+}
+
 // ------------------------------------------------------------------------------------------------ host
 // Tile-N choice.  Depends only on (ldw, M, kind) so the packer and the dispatcher always agree; the chosen
 // value also travels explicitly with every call (tc_bn).
@@ -955,9 +994,11 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
 
 template <class AP>
 static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
-                       size_t scratch_bytes, cudaStream_t st) {
+                       size_t scratch_bytes, cudaStream_t st, int taps = 1) {
     if (blob == nullptr || bn <= 0 || bn > 128 || ldw % bn != 0 || ep.Cout % 4 != 0 || K % TC_BK != 0 || ldw > TS_SS_MAXC) return DEFT_EINVAL;
-    const int nkb = K / TC_BK, nt = ldw / bn;
+    const bool f16 = tc_blob_is_f16(K, taps, bn) && !(flags & DEFT_FLAG_TF32X1);
+    if (tc_blob_is_f16(K, taps, bn) && !f16) return DEFT_EINVAL;      // the image is packed for 3xFP16: no single-pass TF32 variant of it
+    const int nkb = K / (f16 ? 64 : TC_BK), nt = ldw / bn;
     int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
     if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
     if (splits > 1) splits = ceil_div(nkb, ceil_div(nkb, splits));
@@ -966,8 +1007,9 @@ static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     int rc = DEFT_EINVAL;
 #define TS_CASE(BNV)                                                                          \
     case BNV:                                                                                 \
-        rc = x1 ? ts_launch<AP, BNV, 1>(ap, blob, nkb, M, nt, splits, epi, st)                \
-                : ts_launch<AP, BNV, 3>(ap, blob, nkb, M, nt, splits, epi, st);               \
+        rc = f16 ? ts_launch<AP, BNV, 6>(ap, blob, nkb, M, nt, splits, epi, st)               \
+           : x1  ? ts_launch<AP, BNV, 1>(ap, blob, nkb, M, nt, splits, epi, st)               \
+                 : ts_launch<AP, BNV, 3>(ap, blob, nkb, M, nt, splits, epi, st);              \
         break;
     switch (bn) {
         TS_CASE(128)
@@ -1035,7 +1077,10 @@ static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, 
     if (enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ap.src[0]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return DEFT_EINVAL;
-    const int nkb = K / TC_BK, nt = ldw / bn, ncb = ap.Ctot / TC_BK;
+    const bool f16 = tc_blob_is_f16(K, 9, bn);
+    if (f16 && (flags & DEFT_FLAG_TF32X1)) return DEFT_EINVAL;
+    const int kch = f16 ? 64 : TC_BK;
+    const int nkb = K / kch, nt = ldw / bn, ncb = ap.Ctot / kch;
     const int m_tiles = ap.N * t.tiles_x * t.tiles_y;
     int splits = tc_pick_splits(m_tiles * nt, nkb);
     if (splits > ncb) splits = ncb;
@@ -1046,8 +1091,9 @@ static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, 
     int rc = DEFT_EINVAL;
 #define TP_CASE(BNV)                                                                                   \
     case BNV:                                                                                          \
-        rc = x1 ? ts_launch<TsPatchAP, BNV, 1>(t, blob, nkb, M, nt, splits, epi, st, m_tiles)          \
-                : ts_launch<TsPatchAP, BNV, 3>(t, blob, nkb, M, nt, splits, epi, st, m_tiles);         \
+        rc = f16 ? ts_launch<TsPatchAP, BNV, 6>(t, blob, nkb, M, nt, splits, epi, st, m_tiles)         \
+           : x1  ? ts_launch<TsPatchAP, BNV, 1>(t, blob, nkb, M, nt, splits, epi, st, m_tiles)         \
+                 : ts_launch<TsPatchAP, BNV, 3>(t, blob, nkb, M, nt, splits, epi, st, m_tiles);        \
         break;
     switch (bn) {
         TP_CASE(128)
@@ -1081,9 +1127,13 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
             t.a = ap;
             t.taps = ap.KH * ap.KW;
             t.ncb = ap.Ctot / TC_BK;
-            return ts_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+            if (tc_blob_is_f16(K, t.taps, bn))                 // 64-channel k-blocks must not straddle sources
+                for (int i = 0; i < ap.nsrc; ++i)
+                    if (ap.c[i] % 64 != 0) return DEFT_EINVAL;
+            return ts_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st, t.taps);
         }
     }
+    if (tc_blob_is_f16(K, ap.KH * ap.KW, bn)) return DEFT_EINVAL;   // the smem-operand kernel below reads 3xTF32 images only
     if (ap.nsrc == 1 && ap.Ctot % TC_BK == 0 && ap.KH * ap.KW <= 9) {
         // fast path: single source, channel-block-major K (what tc_k_perm_taps prescribes for Ctot % 32 == 0) or 1x1
         return tc_dispatch(make_fast_ap(ap), blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
@@ -1103,8 +1153,9 @@ int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, 
     if (ts_dcn && ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
         TsDcnAP d{};
         d.a = ap;
-        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st, 9);
     }
+    if (tc_blob_is_f16(K, 9, bn)) return DEFT_EINVAL;
     TcDcnAP t{};
     t.a = ap;
     t.K = K;
@@ -1115,8 +1166,9 @@ int tc_pair_dispatch(const PairAP& ap, const float* blob, int bn, int ldw, int K
     if (ts_enabled() && bn <= 128 && K % TC_BK == 0) {
         TsPairAP d{};
         d.a = ap;
-        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, nullptr, 0, st);
+        return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, nullptr, 0, st, 1);
     }
+    if (tc_blob_is_f16(K, 1, bn)) return DEFT_EINVAL;
     TcPairAP t{};
     t.a = ap;
     t.K = K;
@@ -1139,6 +1191,15 @@ int tc_heads_dispatch(const ConvAP& ap, const float* blob, int K, int M, const H
 }
 
 int tc_pack_weights(const float* wp, int ldw, int K, int bn, int taps, float* blob, cudaStream_t st) {
+    if (tc_blob_is_f16(K, taps, bn)) {
+        const int nkb16 = K / 64, nt16 = ldw / bn;
+        size_t total16 = (size_t)nt16 * nkb16 * bn * 64;
+        int blocks16 = (int)((total16 + 255) / 256);
+        if (blocks16 > TC_NUM_SMS * 8) blocks16 = TC_NUM_SMS * 8;
+        tc_pack_weights_f16_kernel<<<blocks16, 256, 0, st>>>(wp, ldw, K, bn, nkb16, nt16, taps > 1 ? taps : 0, reinterpret_cast<__half*>(blob));
+        DEFT_CHECK_LAUNCH("tc_pack_weights_f16");
+        return DEFT_OK;
+    }
     int nkb = ceil_div(K, TC_BK), nt = ldw / bn;
     size_t total = (size_t)nt * nkb * bn * TC_BK;
     int blocks = (int)((total + 255) / 256);

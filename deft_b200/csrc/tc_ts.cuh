@@ -23,6 +23,31 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// 3xFP16 split of 16 consecutive K elements of one row: x = hi + lo + O(2^-22 x), hi = fp16(x), lo = fp16(x - hi).  A 32-bit
+// TMEM cell holds two consecutive K elements, the EVEN one in the low half (measured: tools/exp_f16ts.py).
+__device__ __forceinline__ void split_f16x3(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// cute::UMMA::InstrDescriptor for kind::f16: fp16 A and B (format 0), fp32 accumulate, K-major, M = 128, N = bn
+__host__ __device__ constexpr uint32_t make_idesc_f16(int bn) { return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -57,6 +82,7 @@ struct TsConvAP {
     static constexpr int kExtraSmemBytes = 64 + 64 * 16;
     const int* toff_;
     const TsSrcEntry* cbsrc_;
+    __device__ __forceinline__ int ktaps() const { return taps; }
     __device__ __forceinline__ void setup_once(unsigned char* extra) {
         int* toff = reinterpret_cast<int*>(extra);
         TsSrcEntry* cbsrc = reinterpret_cast<TsSrcEntry*>(extra + 64);
@@ -128,6 +154,7 @@ struct TsDcnAP {
     const int* tabB_;
     const float4* tabW_;
     int rowpitch_;
+    __device__ __forceinline__ int ktaps() const { return 9; }
     __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void tile_init(int m0, int M, unsigned char* extra, int, int, int4*) {
         float4* tabW = reinterpret_cast<float4*>(extra);
@@ -204,6 +231,7 @@ struct TsPairAP {
     static constexpr bool kPatch = false;
     PairAP a;
     static constexpr int kExtraSmemBytes = 0;
+    __device__ __forceinline__ int ktaps() const { return 1; }
     __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int quad, int lane, int4* meta) {
         const int p = m0 + quad * 32 + lane;
@@ -261,6 +289,7 @@ struct TsPatchAP {
     alignas(64) CUtensorMap tmap;                                  // dims {C, W, H, N} of the NHWC source
     int H, W, tiles_x, tiles_y;
     // interface stubs (the patch path has its own producer loop)
+    __device__ __forceinline__ int ktaps() const { return 9; }
     __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
     __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
@@ -272,6 +301,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
+// dynamic shared memory the TS kernel may ask for: the 227 KB opt-in limit minus its 64 bytes of static shared memory (progress board)
+constexpr int TS_SMEM_LIMIT = TC_SMEM_LIMIT - 128;
 constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across producer warp groups
 // Two MMA issuer warps alternate k-blocks (tcgen05.mma issue blocks the issuing thread, so one issuer leaves the tensor
 // pipe idle during its own barrier waits and commits: 53 -> 43 us on the 64->64 3x3 layer).  Each issuer accumulates
@@ -288,7 +319,12 @@ constexpr int TS_ISSUERS = 2;
 
 template <int BN, int NPASS>
 struct TsCfg {
-    static constexpr int ACOLS = NPASS == 3 ? 64 : 32;                 // TMEM columns of one A stage (hi [+ lo])
+    // NPASS: 1 = single TF32 pass, 3 = 3xTF32 (k-block = 32 channels), 6 = 3xFP16 (kind::f16, k-block = 64 channels: the same
+    // 64 TMEM columns and the same 128-byte weight rows hold twice the K, every MMA covers K = 16 instead of 8).
+    static constexpr bool F16 = NPASS == 6;
+    static constexpr int PASSES = F16 ? 3 : NPASS;
+    static constexpr int KCH = F16 ? 64 : 32;                          // channels per k-block
+    static constexpr int ACOLS = PASSES == 3 ? 64 : 32;                // TMEM columns of one A stage (hi [+ lo])
     // Issuer warps: two, alternating k-blocks (a 128x64x8 MMA executes in ~32 cycles but costs ~46 to issue, and an
     // issuer also pays its own barrier waits and commits serially).  r2 tried ONE issuer for N = 128 so that the two
     // accumulator sets fit twice in TMEM (double-buffered epilogue): the pipe, at its floor with two issuers (766 cycles
@@ -307,7 +343,8 @@ struct TsCfg {
     static constexpr int SA_RAW = (512 - A0) / ACOLS;
     static constexpr int SA = SA_RAW > 6 ? 6 : SA_RAW;                  // A ring depth
     static constexpr int B_TILE = BN * 128;
-    static constexpr int B_STAGE = NPASS == 3 ? 2 * B_TILE : B_TILE;
+    static constexpr int B_STAGE = PASSES == 3 ? 2 * B_TILE : B_TILE;
+    static constexpr int P_STAGE = F16 ? 2 * TP_STAGE_BYTES : TP_STAGE_BYTES;   // halo patch of one k-block's channels
 };
 
 // Accumulator tile -> output, 32 (or BN) columns at a time.  tcgen05.ld hands every lane one accumulator ROW; storing
@@ -414,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     unsigned char* smem = smem_raw + pad;
     // layout: [patch ring: ps x TP_STAGE_BYTES (patch producer only)] [sb x B_STAGE] [barriers + tmem slot: 512 B] [epilogue stages]
     //         [producer stages (gather producers only)] [AP extra]
-    const uint32_t patch_bytes = kPatch ? (uint32_t)ps * TP_STAGE_BYTES : 0u;
+    const uint32_t patch_bytes = kPatch ? (uint32_t)ps * Cfg::P_STAGE : 0u;
     const uint32_t sbase = raw_addr + pad + patch_bytes;  // weight ring
     const uint32_t bar_base = sbase + (uint32_t)sb * Cfg::B_STAGE;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -487,7 +524,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                         }
                         const int gc = gc0 + c;
                         mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
-                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * TP_STAGE_BYTES);
+                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * Cfg::P_STAGE);
                         last_c = c;
                     }
                     const int gk = gk0 + i;
@@ -511,7 +548,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     __syncwarp();                              // converged before the .aligned tcgen05.st
                     tc_fence_after();
                     if (tid == grp * 128) TC_TRACE(1, gk, 2);
-                    if (!(dbg & 4)) {
+                    if constexpr (Cfg::F16) {
+                        // 64 channels per k-block: the two 32-channel halo sub-patches of the stage, one after the other
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h == 1) {
+                                const float* prow1 = prow + TP_STAGE_BYTES / 4;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow1 + ((q ^ sw) << 2));
+                            }
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const float v[16] = {x[4 * q].x, x[4 * q].y, x[4 * q].z, x[4 * q].w, x[4 * q + 1].x, x[4 * q + 1].y, x[4 * q + 1].z, x[4 * q + 1].w,
+                                                     x[4 * q + 2].x, x[4 * q + 2].y, x[4 * q + 2].z, x[4 * q + 2].w, x[4 * q + 3].x, x[4 * q + 3].y, x[4 * q + 3].z, x[4 * q + 3].w};
+                                uint32_t hi[8], lo[8];
+                                split_f16x3(v, hi, lo);
+                                tmem_st8u(acol + (uint32_t)(h * 16 + q * 8), hi);
+                                tmem_st8u(acol + 32u + (uint32_t)(h * 16 + q * 8), lo);
+                            }
+                        }
+                    } else if (!(dbg & 4)) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float v[8] = {x[2 * q].x, x[2 * q].y, x[2 * q].z, x[2 * q].w, x[2 * q + 1].x, x[2 * q + 1].y, x[2 * q + 1].z, x[2 * q + 1].w};
@@ -561,6 +617,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
                 const uint32_t acol = tmem_base + lane_addr + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
                 if (tid == grp * 128) TC_TRACE(1, gk, 0);
+                if constexpr (Cfg::F16) {
+                    // k-block = 64 channels = two 32-channel fills through the same private stage.  K order is (64-channel block,
+                    // tap, channel); fill() counts 32-channel blocks: (2 c + h) * taps + tap.
+                    const int taps = ap.ktaps();
+                    const int kbg = kb0 + i, c64 = kbg / taps, tap = kbg - c64 * taps;
+                    ap.fill((2 * c64) * taps + tap, quad, lane, meta, stage);
+                    __syncwarp();
+                    if (tid == grp * 128) TC_TRACE(1, gk, 1);
+                    mbar_wait(a_empty(sa), pa ^ 1u, 2, gk, quad == 0 ? prog : nullptr, grp);
+                    __syncwarp();                              // converged before the .aligned tcgen05.st
+                    tc_fence_after();
+                    if (tid == grp * 128) TC_TRACE(1, gk, 2);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1) {
+                            __syncwarp();                      // everyone has read the first half out of the stage
+                            ap.fill((2 * c64 + 1) * taps + tap, quad, lane, meta, stage);
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {          // lane = row: 16 columns at a time
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(stage + lane * TS_STAGE_LD + q * 16 + j * 4);
+                                v[4 * j] = t4.x; v[4 * j + 1] = t4.y; v[4 * j + 2] = t4.z; v[4 * j + 3] = t4.w;
+                            }
+                            uint32_t hi[8], lo[8];
+                            split_f16x3(v, hi, lo);
+                            tmem_st8u(acol + (uint32_t)(h * 16 + q * 8), hi);
+                            tmem_st8u(acol + 32u + (uint32_t)(h * 16 + q * 8), lo);
+                        }
+                    }
+                } else {
                 if (!(dbg & 2)) ap.fill(kb0 + i, quad, lane, meta, stage);     // coalesced loads -> private smem stage
                 __syncwarp();
                 if (tid == grp * 128) TC_TRACE(1, gk, 1);
@@ -585,6 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                             tmem_st8(acol + 32u + (uint32_t)(q * 8), lo);
                         }
                     }
+                }
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -626,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             // The tensor core adds every MMA into the fp32 accumulator with round-toward-zero (measured: tools/tc_bias.py, a
             // gain of -1.6e-8 per accumulate step, e.g. -6.8e-6 at K = 2304).  An accumulator of this tile took
             // 4 * NPASS * ceil(nkb / ISS) steps; the expected shrink is undone here (DEFT_TC_RZ_COMP=0 disables it).
-            const float rz_gain = 1.0f + rz_comp * (float)(4 * NPASS * ((nkb + Cfg::ISS - 1) / Cfg::ISS));
+            const float rz_gain = 1.0f + rz_comp * (float)(4 * Cfg::PASSES * ((nkb + Cfg::ISS - 1) / Cfg::ISS));
             TsRowMap rm{};
             rm.M = M;
             if constexpr (kPatch) {
@@ -650,7 +741,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
         // ===================== two MMA issuer warps (A from TMEM, B from smem), alternating k-blocks =====================
         // tcgen05.mma issue blocks the issuing thread for roughly the MMA's duration (measured ~46 cycles for 128x64x8).
         // Issuer w owns k-blocks w, w+2, ... of every tile and accumulator column block w of the tile's set.
-        constexpr uint32_t idesc = make_idesc(BN);
+        constexpr uint32_t idesc = Cfg::F16 ? make_idesc_f16(BN) : make_idesc(BN);
         const int w = warp - TC_MMA_WARP;
         int iter = 0, gk0 = 0;
         for (int t = (w < Cfg::ISS) ? (int)blockIdx.x : ts.total; t < ts.total; t += gridDim.x, ++iter) {
@@ -694,6 +785,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                             // then the A_lo x B_hi correction into the first block
                             umma_tf32_ts(tmem_acc, a_hi + k * 8, db_hi, make_idesc(2 * BN), (i > i_first || k > 0) ? 1u : 0u);
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, 1u);
+                        } else if constexpr (Cfg::F16) {
+                            const uint64_t db_lo = make_smem_desc(b_lo + k * 32);      // 16 fp16 = 32 bytes per k-step, 8 TMEM cells
+                            umma_f16_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
+                            umma_f16_ts(tmem_acc, a_hi + k * 8, db_lo, idesc, 1u);
+                            umma_f16_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, 1u);
                         } else if (NPASS == 3) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
@@ -757,8 +853,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     const int s = gc % ps;
                     mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc, prog, 8);
                     if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
-                        tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
+                        if constexpr (Cfg::F16) {          // 64 channels per k-block: two 32-channel boxes into the two halves of the stage
+                            mbar_arrive_expect_tx(p_full(s), (uint32_t)(2 * TP_BOX_BYTES));
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * Cfg::P_STAGE, &ap_param.tmap, (c0 + c) * 64, x0, y0, n, p_full(s));
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * Cfg::P_STAGE + TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * 64 + 32, x0, y0, n, p_full(s));
+                        } else {
+                            mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
+                        }
                     }
                     __syncwarp();
                 }
@@ -780,8 +882,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
 template <class AP, int BN, int NPASS>
 static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st, int m_tiles_override = 0) {
     using Cfg = TsCfg<BN, NPASS>;
-    constexpr int ps = AP::kPatch ? TP_MAX_STAGES : 0;
-    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * TP_STAGE_BYTES : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
+    constexpr int ps = AP::kPatch ? (Cfg::F16 ? 2 : TP_MAX_STAGES) : 0;
+    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * Cfg::P_STAGE : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
     if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, 9) * 9;      // whole channel blocks per split
@@ -790,7 +892,7 @@ static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tile
     ts.n_tiles = n_tiles;
     ts.nkb_total = nkb;
     ts.total = ts.m_tiles * ts.n_tiles * ts.splits;
-    int sb = (TC_SMEM_LIMIT - fixed) / Cfg::B_STAGE;
+    int sb = (TS_SMEM_LIMIT - fixed) / Cfg::B_STAGE;
     if (sb > 8) sb = 8;
     if (std::is_same<AP, TsDcnAP>::value) {
         // The DCN gather goes through L1: claim only as much shared memory as the weight ring needs (DEFT_DCN_SB
@@ -803,7 +905,7 @@ static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tile
     size_t smem = (size_t)sb * Cfg::B_STAGE + fixed;
     static size_t granted[DEFT_MAX_DEVICES] = {};
     {
-        const int rc_attr = ensure_dyn_smem(tc_ts_kernel<AP, BN, NPASS>, TC_SMEM_LIMIT, granted, "tc_ts_kernel");
+        const int rc_attr = ensure_dyn_smem(tc_ts_kernel<AP, BN, NPASS>, TS_SMEM_LIMIT, granted, "tc_ts_kernel");
         if (rc_attr != DEFT_OK) return rc_attr;
     }
     if (std::is_same<AP, TsDcnAP>::value) {

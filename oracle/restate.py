@@ -376,6 +376,9 @@ def afe_loss(inp, target, mask0, mask1, max_object):
 
 
 # --------------------------------------------------------------------------- f1: recorder decay + per-track median
+# PARITY UNPINNED BY A RUNNING REFERENCE: utils/tracker.py cannot be imported here (it needs `lap`, `cython_bbox`, `progress`
+# and parses sys.argv at import: SURVEY.md section 8(c)), and the reference holds no test vectors for it.  The two functions
+# below restate the cited lines; tests/test_oracle_cpu.py checks their row-selection / decay rules against hand-built cases.
 def recorder_similarity(aff_by_frame, frame_index, dataset="mot", decay=1.0, decay2=0.01):
     """FeatureRecorder.update's loop (utils/tracker.py:76-90; constants 22-25): aff_by_frame {pre_index: np[n_pre, m+1]}
     (forward_stacker_features(..., fill_up_column=False)) -> {pre_index: similarity * delta}, float32 like the reference
@@ -442,6 +445,9 @@ def warp_affine_bilinear(img_u8_hwc, inv_affine, H, W):
 
 
 # --------------------------------------------------------------------------- f3: motion fusion + linear assignment
+# PARITY UNPINNED BY A RUNNING REFERENCE: utils/matching.py needs `lap` (requirements.txt:14, unpinned, absent) and
+# `cython_bbox`.  fuse_motion is restated line by line; lapjv(extend_cost, cost_limit) is restated as the exact solution of
+# lap's extended problem and checked against brute force (tests/test_oracle_cpu.py).
 CHI2INV95_2 = 5.9915                                         # kalman_filter.py:13-15 (chi2inv95[2])
 
 

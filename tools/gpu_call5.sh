@@ -10,4 +10,10 @@ DEFT_TC_RZ_COMP=0 timeout 900 python bench.py --steps 50 --warmup 10 > $O/bench_
 timeout 600 python bench.py --config c4 --steps 150 --warmup 10 --no-cpu-baseline > $O/bench_c4.json 2> $O/bench_c4.err
 timeout 600 python bench.py --config c4 --streams 3 --steps 60 --warmup 10 --no-cpu-baseline > $O/bench_c4_3streams.json 2> $O/bench_c4_3streams.err
 timeout 600 python bench.py --config c3 --steps 150 --warmup 10 --no-cpu-baseline > $O/bench_c3.json 2> $O/bench_c3.err
-cat $O/tc_bias.log; tail -2 $O/pytest_ops.log $O/pytest_r2.log $O/pytest_frame.log; cut -c1-110 $O/diag.log; for f in $O/bench_*.json; do echo $f; head -c 300 $f; echo; done; grep -h "stall\|roles" $O/* | head
+# ---- 3xFP16 mode (opt-in): numerics vs the SIMT engine, per-layer time, frame rate + parity
+DEFT_TC_F16=1 timeout 400 python tools/tc_diag.py c1x1_k256_n256 c3x3_64_64 c3x3_128_128_s2 c3x3_512_512 root_448_128 dcn_64_64 dcn_512_256 dcn_128_128 big_c3x3_64_64 big_dcn_64_64 c3x3_256_256_l4 > $O/diag_f16.log 2>&1
+DEFT_TC_F16=1 timeout 200 python tools/tc_perf.py > $O/perf_f16.log 2>&1
+timeout 200 python tools/tc_perf.py > $O/perf_tf32.log 2>&1
+DEFT_TC_F16=1 timeout 900 python bench.py --steps 100 --warmup 10 > $O/bench_c2_f16.json 2> $O/bench_c2_f16.err
+DEFT_TC_F16=1 timeout 300 python -m pytest tests/test_gpu_ops.py -x -q -m gpu > $O/pytest_ops_f16.log 2>&1
+echo DONE
