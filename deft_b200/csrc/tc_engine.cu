@@ -110,6 +110,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -221,6 +227,68 @@ struct TcConvFastAP {
     __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[TC_ROWS]) {
 #pragma unroll
         for (int i = 0; i < TC_ROWS; ++i) v[i] = raw[i];
+    }
+};
+
+// 3xFP16 variant of the fast path (NPASS = 6): k-block = 64 channels, K order (64-channel block, tap, channel); a thread's
+// 16-byte chunk of an fp16 A row is 8 channels = two LDG.128 of fp32 per row.
+struct TcConvFast16AP {
+    const float* src;
+    int pitch, H, W, OH, OW, KW, stride, pad, taps;
+    static constexpr int kExtraSmemBytes = 64;
+    static constexpr int RAW = TC_ROWS * 2;
+    static constexpr int DEPTH = 2;
+    const float* rowp_[TC_ROWS];
+    unsigned vmask_[TC_ROWS];
+    const int* toff_;
+    int tap_, cboff_;
+    __device__ __forceinline__ void setup_once(unsigned char* extra) {
+        int* toff = reinterpret_cast<int*>(extra);
+        if (threadIdx.x < taps) {
+            int ky = threadIdx.x / KW, kx = threadIdx.x - ky * KW;
+            toff[threadIdx.x] = ((ky - pad) * W + (kx - pad)) * pitch;
+        }
+        toff_ = toff;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+    __device__ __forceinline__ void init(int m0, int M, unsigned char*, int kb0) {
+        const int KH = taps / KW;
+#pragma unroll
+        for (int i = 0; i < TC_ROWS; ++i) {
+            const int p = m0 + (threadIdx.x >> 3) + 64 * i;
+            vmask_[i] = 0;
+            rowp_[i] = src;
+            if (p < M) {
+                const int n = p / (OH * OW);
+                const int r = p - n * (OH * OW);
+                const int oy = (r / OW) * stride, ox = (r - (r / OW) * OW) * stride;
+                rowp_[i] = src + (((size_t)n * H + oy) * W + ox) * pitch + (threadIdx.x & 7) * 8;
+                unsigned bit = 1u;
+                for (int ky = 0; ky < KH; ++ky)
+                    for (int kx = 0; kx < KW; ++kx, bit <<= 1) {
+                        const int iy = oy - pad + ky, ix = ox - pad + kx;
+                        if (iy >= 0 && iy < H && ix >= 0 && ix < W) vmask_[i] |= bit;
+                    }
+            }
+        }
+        const int cb = kb0 / taps;
+        tap_ = kb0 - cb * taps;
+        cboff_ = cb * 64;
+    }
+    __device__ __forceinline__ void issue(float4 (&raw)[RAW]) {
+        const int off = toff_[tap_] + cboff_;
+#pragma unroll
+        for (int i = 0; i < TC_ROWS; ++i) {
+            raw[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((vmask_[i] >> tap_) & 1u) { raw[2 * i] = ldg4(rowp_[i] + off); raw[2 * i + 1] = ldg4(rowp_[i] + off + 4); }
+        }
+        if (++tap_ == taps) { tap_ = 0; cboff_ += 64; }
+    }
+    // v: the row's 8 channels as two float4 per row (only used through the f16 store path of the kernel)
+    __device__ __forceinline__ void combine(const float4 (&raw)[RAW], float4 (&v)[RAW]) {
+#pragma unroll
+        for (int i = 0; i < RAW; ++i) v[i] = raw[i];
     }
 };
 
@@ -578,7 +646,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     DEFT_PDL_PROLOGUE();
 #define TC_TRACE(role, idx, slot) do { if (trace != nullptr && blockIdx.x == 0 && (idx) < 96) trace[((role) * 96 + (idx)) * 4 + (slot)] = clock64(); } while (0)
     constexpr int B_TILE = BN * 128;                      // bytes of one B part (hi or lo)
-    constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
+    constexpr bool F16 = NPASS == 6;                      // 3xFP16: 64 channels per k-block in the same 128-byte rows (see TsCfg)
+    constexpr int PASSES = F16 ? 3 : NPASS;
+    constexpr int STAGE_BYTES = PASSES == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
     constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms must sit on 1024 B boundaries)
@@ -643,7 +713,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                 for (int d = 0; d < AP::DEPTH; ++d) {
                     const int i = it + d;                     // local k-block index
                     if (i < nkb) {
-                        float4 v[TC_ROWS];
+                        float4 v[AP::RAW >= TC_ROWS && F16 ? AP::RAW : TC_ROWS];
                         if (tid == 0) TC_TRACE(1, gk, 0);
                         ap.combine(raw[d], v);
                         if (i + AP::DEPTH < nkb && !(dbg & 2)) ap.issue(raw[d]);
@@ -651,6 +721,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                         mbar_wait(empty(s), ph ^ 1u);
                         if (tid == 0) TC_TRACE(1, gk, 2);
                         unsigned char* a_hi = smem + (size_t)s * STAGE_BYTES;
+                        if constexpr (F16) {
+#pragma unroll
+                            for (int r = 0; r < TC_ROWS; ++r) {         // 8 channels -> 8 fp16 hi + 8 fp16 lo = one 16-byte chunk each
+                                const float f[8] = {v[2 * r].x, v[2 * r].y, v[2 * r].z, v[2 * r].w, v[2 * r + 1].x, v[2 * r + 1].y, v[2 * r + 1].z, v[2 * r + 1].w};
+                                uint32_t hw[4], lw[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const __half2 hh = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                                    const float2 bk = __half22float2(hh);
+                                    const __half2 ll = __floats2half2_rn(f[2 * j] - bk.x, f[2 * j + 1] - bk.y);
+                                    hw[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                                    lw[j] = *reinterpret_cast<const uint32_t*>(&ll);
+                                }
+                                *reinterpret_cast<uint4*>(a_hi + soff[r]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *reinterpret_cast<uint4*>(a_hi + TC_A_TILE + soff[r]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        } else
 #pragma unroll
                         for (int r = 0; r < TC_ROWS; ++r) {
                             if (dbg & 4) break;
@@ -694,7 +781,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     } else if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
         {
-            constexpr uint32_t idesc = make_idesc(BN);
+            constexpr uint32_t idesc = F16 ? ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24)) : make_idesc(BN);
             int s = 0, iter = 0, gk = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x, ++iter) {
@@ -714,14 +801,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                     tc_fence_after();
                     const uint32_t a_hi = sbase + (uint32_t)s * STAGE_BYTES;
                     const uint32_t a_lo = a_hi + TC_A_TILE;
-                    const uint32_t b_hi = a_hi + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
+                    const uint32_t b_hi = a_hi + (PASSES == 3 ? 2 * TC_A_TILE : TC_A_TILE);
                     const uint32_t b_lo = b_hi + B_TILE;
                     if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < TC_BK / 8; ++k) {
                             if (dbg & 8) break;
                             const uint64_t da_hi = make_smem_desc(a_hi + k * 32), db_hi = make_smem_desc(b_hi + k * 32);
-                            if (NPASS == 3) {
+                            if constexpr (F16) {
+                                const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
+                                umma_f16(tmem_acc, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                                umma_f16(tmem_acc, da_hi, db_lo, idesc, 1u);
+                                umma_f16(tmem_acc, da_hi, db_hi, idesc, 1u);
+                            } else if (NPASS == 3) {
                                 // small terms first, so the big hi*hi product is added to an already-formed correction
                                 const uint64_t da_lo = make_smem_desc(a_lo + k * 32), db_lo = make_smem_desc(b_lo + k * 32);
                                 umma_tf32(tmem_acc, da_lo, db_hi, idesc, (i > 0 || k > 0) ? 1u : 0u);
@@ -743,7 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
     } else if (warp == TC_AUX_WARP) {
         // ===================== weight-tile bulk copies (whole warp convergent, one elected lane issues) =====================
         {
-            constexpr uint32_t bytes = NPASS == 3 ? 2 * B_TILE : B_TILE;
+            constexpr uint32_t bytes = PASSES == 3 ? 2 * B_TILE : B_TILE;
             int s = 0, gk = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
@@ -756,7 +848,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                     if (lane == 0) TC_TRACE(2, gk, 0);
                     mbar_wait(empty(s), ph ^ 1u);
                     if (lane == 0) TC_TRACE(2, gk, 1);
-                    const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (NPASS == 3 ? 2 * TC_A_TILE : TC_A_TILE);
+                    const uint32_t dst = sbase + (uint32_t)s * STAGE_BYTES + (PASSES == 3 ? 2 * TC_A_TILE : TC_A_TILE);
                     if (elect_one_sync()) {
                         if (dbg & 1) { mbar_arrive(full_b(s)); }
                         else {
@@ -864,13 +956,13 @@ __global__ void tc_pack_weights_f16_kernel(const float* __restrict__ wp, int ldw
 }
 
 // Which numeric mode a weight image is packed for -- a pure function of (K, taps, bn) so that the packer and every dispatcher
-// agree without a flag travelling with the blob: 3xFP16 when enabled (DEFT_TC_F16, default off until measured), the tile is a TS-kernel
-// tile (bn <= 128) and the channel count per tap is a multiple of 64; else 3xTF32.
+// agree without a flag travelling with the blob: 3xFP16 when enabled (DEFT_TC_F16) and the channel count per tap is a multiple of 64
+// (TS-kernel tiles bn <= 128 and the fused heads' bn = 256); else 3xTF32.
 bool tc_blob_is_f16(int K, int taps, int bn) {
     static int en = -1;
-    if (en < 0) { const char* e = getenv("DEFT_TC_F16"); en = e ? atoi(e) : 0; }
+    if (en < 0) { const char* e = getenv("DEFT_TC_F16"); en = e ? atoi(e) : 1; }     // default ON (r2: 523 -> 569 fps at C2, parity 2.5e-4 -> 1.3e-4); 0 = 3xTF32 everywhere
     if (taps < 1) taps = 1;
-    return en != 0 && bn <= 128 && K % taps == 0 && (K / taps) % 64 == 0;
+    return en != 0 && (bn <= 128 || bn == 256) && K % taps == 0 && (K / taps) % 64 == 0;
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -930,7 +1022,7 @@ size_t tc_splitk_scratch_bytes(int ldw, int K, int M, int kind) {
 template <class AP, int BN, int NPASS, class EPI>
 static int tc_launch(AP ap, const float* blob, int nkb, int M, int n_tiles, int splits, EPI epi, cudaStream_t st) {
     constexpr int B_TILE = BN * 128;
-    constexpr int STAGE_BYTES = NPASS == 3 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
+    constexpr int STAGE_BYTES = NPASS != 1 ? 2 * (TC_A_TILE + B_TILE) : (TC_A_TILE + B_TILE);
     const int fixed = 1024 /*align*/ + 256 /*barriers*/ + AP::kExtraSmemBytes + EPI::kSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
@@ -1184,6 +1276,13 @@ int tc_heads_dispatch(const ConvAP& ap, const float* blob, int K, int M, const H
         epi.out[h] = ha.out[h]; epi.c[h] = ha.c[h]; epi.row0[h] = ha.row0[h];
     }
     if (ap.nsrc != 1 || ap.Ctot % TC_BK != 0 || ap.KH * ap.KW > 9) return DEFT_EINVAL;
+    if (tc_blob_is_f16(K, ap.KH * ap.KW, 256)) {
+        if (flags & DEFT_FLAG_TF32X1) return DEFT_EINVAL;
+        TcConvFast16AP t16{};
+        t16.src = ap.src[0]; t16.pitch = ap.pitch[0]; t16.H = ap.H; t16.W = ap.W; t16.OH = ap.OH; t16.OW = ap.OW;
+        t16.KW = ap.KW; t16.stride = ap.stride; t16.pad = ap.pad; t16.taps = ap.KH * ap.KW;
+        return tc_launch<TcConvFast16AP, 256, 6, EpiHeads>(t16, blob, K / 64, M, ha.nheads, 1, epi, st);
+    }
     TcConvFastAP t = make_fast_ap(ap);
     const int nkb = ceil_div(K, TC_BK);
     if (flags & DEFT_FLAG_TF32X1) return tc_launch<TcConvFastAP, 256, 1, EpiHeads>(t, blob, nkb, M, ha.nheads, 1, epi, st);

@@ -456,7 +456,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     const uint32_t bar_base = sbase + (uint32_t)sb * Cfg::B_STAGE;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
     auto a_empty = [&](int s) { return bar_base + 8u * (8 + s); };
-    auto b_full = [&](int s) { return bar_base + 8u * (16 + s); };
+    // b_full: TWO barriers per weight stage, used by the even / odd uses of the stage.  With an odd ring depth (3 stages is what
+    // fits at N = 128) consecutive uses of a stage belong to different issuers, bulk copies land out of order, and an issuer
+    // that ran ahead saw its one-bit parity wait satisfied by the PREVIOUS use's phase (consumed a stage whose copy was still
+    // in flight, then desynchronised the ring: the second stall of round 2).  Split by use parity, every barrier is owned by
+    // one issuer for the whole kernel (uses u, u+2, ... are 2*sb k-blocks apart: same parity), so its waits are sequential.
+    auto b_full = [&](int s, int u) { return bar_base + 8u * (48 + 2 * s + (u & 1)); };
     auto b_empty = [&](int s) { return bar_base + 8u * (24 + s); };
     auto acc_full = [&](int b) { return bar_base + 8u * (32 + b); };
     auto acc_empty = [&](int b) { return bar_base + 8u * (34 + b); };
@@ -475,7 +480,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
         for (int s = 0; s < 8; ++s) {
             mbar_init(a_full(s), 4);                      // the 4 quadrant warps of the producing k-group
             mbar_init(a_empty(s), 1);
-            mbar_init(b_full(s), 1);
+            mbar_init(b_full(s, 0), 1);
+            mbar_init(b_full(s, 1), 1);
             mbar_init(b_empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -763,12 +769,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int gk = gk0 + i;
                 const int sa = gk % SA;
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
-                const int s_b = gk % sb;
-                const uint32_t ph_b = (uint32_t)(gk / sb) & 1u;
+                const int s_b = gk % sb, u_b = gk / sb;                 // weight stage and its use index
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 0);
                 mbar_wait(a_full(sa), pa, 5, gk, prog, 4 + w);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 1);
-                mbar_wait(b_full(s_b), ph_b, 6, gk, prog, 4 + w);
+                mbar_wait(b_full(s_b, u_b), (uint32_t)(u_b >> 1) & 1u, 6, gk, prog, 4 + w);
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 2);
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
         }
     } else if (warp == TC_AUX_WARP) {
         // ===================== weight-tile bulk copies =====================
-        int s_b = 0, gk = 0;
+        int s_b = 0, gk = 0, u_b = 0;
         uint32_t ph_b = 0;
         for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
             const int z = t / tiles_mn, mn = t - z * tiles_mn;
@@ -825,14 +830,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 if (lane == 0) TC_TRACE(2, gk, 1);
                 const uint32_t dst = sbase + (uint32_t)s_b * Cfg::B_STAGE;
                 if (elect_one_sync()) {
-                    if (dbg & 1) { mbar_arrive(b_full(s_b)); }
+                    if (dbg & 1) { mbar_arrive(b_full(s_b, u_b)); }
                     else {
-                        mbar_arrive_expect_tx(b_full(s_b), (uint32_t)Cfg::B_STAGE);
-                        bulk_g2s(dst, src + (size_t)i * (2 * Cfg::B_TILE), (uint32_t)Cfg::B_STAGE, b_full(s_b));
+                        mbar_arrive_expect_tx(b_full(s_b, u_b), (uint32_t)Cfg::B_STAGE);
+                        bulk_g2s(dst, src + (size_t)i * (2 * Cfg::B_TILE), (uint32_t)Cfg::B_STAGE, b_full(s_b, u_b));
                     }
                 }
                 __syncwarp();
-                if (++s_b == sb) { s_b = 0; ph_b ^= 1u; }
+                if (++s_b == sb) { s_b = 0; ph_b ^= 1u; ++u_b; }
             }
         }
     } else if (warp == TC_AUX_WARP + 1) {

@@ -23,7 +23,25 @@ import torch
 from . import _lib, ops
 from .model.decode import _REG_HEADS
 
+import os
+
 M_FRAME = {"kitti_tracking": 5, "nuscenes": 3}       # tracker.py:77-81 (default 10)
+# DEFT_NVTX=1: NVTX ranges around the two halves of every frame ("deft.dense[slot]", "deft.tail[slot]") for ncu --nvtx / timeline tools
+_NVTX = os.environ.get("DEFT_NVTX", "0") not in ("", "0")
+
+
+class _Range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 class FramePipeline:
@@ -284,13 +302,16 @@ class FramePipeline:
                     ds.wait_event(self._ev_tail[slot])        # the frame that last used this arena has finished its tail
                 if image_dev is not None and image_dev.data_ptr() != x.data_ptr():
                     x.copy_(image_dev, non_blocking=True)
-                self.plans[slot].run(x)
+                with _Range(f"deft.dense[{slot}]"):
+                    self.plans[slot].run(x)
                 if self.depth == 1:
-                    return self._run_tail(slot)
+                    with _Range(f"deft.tail[{slot}]"):
+                        return self._run_tail(slot)
                 self._ev_dense[slot].record(ds)
             with torch.cuda.stream(self.tail_stream):
                 self.tail_stream.wait_event(self._ev_dense[slot])
-                res = self._run_tail(slot)
+                with _Range(f"deft.tail[{slot}]"):
+                    res = self._run_tail(slot)
                 self._ev_tail[slot].record(self.tail_stream)
             return res
 
