@@ -286,7 +286,12 @@ int deft_conv2d_bn_act(const float* const* srcs, const int* src_c, const int* sr
     Epilogue ep{scale, shift, residual, res_pitch, out, out_pitch, Cout, (flags & DEFT_FLAG_RELU) ? 1 : 0};
     int M = N * ap.OH * ap.OW;
     int K = KH * KW * ap.Ctot;
-    // the two HBM-bound 16-channel full-resolution layers (DLA level0 / level1): direct fp32 kernel
+    // the two 16-channel full-resolution layers (DLA level0 / level1): tensor-core path when a weight image packed for it is
+    // supplied (K padded to 192, taps = 1: ops.conv_tc_pack), else the direct fp32 kernel
+    if (nsrc == 1 && src_c[0] == 16 && KH == 3 && KW == 3 && pad == 1 && (flags & DEFT_FLAG_TENSORCORE) && w_tc != nullptr && !(flags & DEFT_FLAG_TF32X1)) {
+        int rc = tc_conv_dispatch(ap, w_tc, tc_bn, ldw, K, M, ep, flags, ws, ws_bytes, to_stream(s));
+        if (rc != DEFT_EINVAL) return rc;
+    }
     if (nsrc == 1 && src_c[0] == 16 && KH == 3 && KW == 3 && pad == 1 && residual == nullptr && !(flags & DEFT_FLAG_NO_DIRECT)) {
         const int relu = (flags & DEFT_FLAG_RELU) ? 1 : 0;
         if (Cout == 16 && ldw == 16 && stride == 1)

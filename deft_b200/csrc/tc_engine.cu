@@ -488,10 +488,10 @@ struct TcPairAP {
 // ------------------------------------------------------------------------------------------------ epilogues
 // 16 epilogue warps: TMEM lane quadrant = warp & 3, column group = warp >> 2.  A warp reads LW columns of its 32
 // rows per tcgen05.ld (one wait per LW columns, not per 8).
+// tmem_ld_issue: the load only; the caller batches several and pays ONE tcgen05.wait::ld (tmem_ld_wait) for all of them.
 template <int LW>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[LW]) {
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[LW]) {
     static_assert(LW == 8 || LW == 16 || LW == 32, "tmem_ld width");
-    uint32_t r[LW];
     if constexpr (LW == 8) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -510,7 +510,13 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[LW]) {
                        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                      : "r"(taddr) : "memory");
     }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int LW>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[LW]) {
+    uint32_t r[LW];
+    tmem_ld_issue<LW>(taddr, r);
+    tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < LW; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -1207,6 +1213,13 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
                      size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
         if (ap.c[i] % 4 != 0) return DEFT_EINVAL;
+    if (ts_enabled() && ap.nsrc == 1 && ap.c[0] == 16 && ap.KH == 3 && ap.KW == 3 && ap.pad == 1 && K == 144) {
+        // the 16-channel full-resolution layers: tap-major pseudo channels, weight image packed from K = 192 (TC_C16_K) with taps = 1
+        TsC16AP t{};
+        t.src = ap.src[0]; t.pitch = ap.pitch[0]; t.N = ap.N; t.H = ap.H; t.W = ap.W; t.OH = ap.OH; t.OW = ap.OW; t.stride = ap.stride;
+        if ((long long)ap.N * ap.H * ap.W >= 2147483647LL / 4) return DEFT_EINVAL;
+        return ts_dispatch(t, blob, bn, ldw, 192, M, ep, flags, nullptr, 0, st, 1);
+    }
     if (ts_enabled() && patch_eligible(ap) && K == 9 * ap.Ctot) {
         int rc = patch_dispatch(ap, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
         if (rc != DEFT_EINVAL) return rc;

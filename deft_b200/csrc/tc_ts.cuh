@@ -138,6 +138,53 @@ struct TsConvAP {
     }
 };
 
+// 3x3 / pad 1 convolution over ONE 16-channel NHWC source (DLA level0 16->16 s1, level1 16->32 s2; r1 ran them as fp32 FMA kernels:
+// 194 us of a 3.4 ms frame).  K is laid out tap-major exactly as the packed weight (k = tap * 16 + c), so a 32-wide pseudo
+// channel block is two taps; the weight image is packed from a copy zero-padded to K = 192 (taps 9..11 do not exist: their
+// operand rows are zeros too).  A row's 128 bytes = 2 taps x 64 B: lanes 0-3 of the row's 8 read tap 2b, lanes 4-7 tap 2b+1.
+struct TsC16AP {
+    static constexpr bool kPatch = false;
+    const float* src;
+    int pitch, N, H, W, OH, OW, stride;
+    static constexpr int kExtraSmemBytes = 0;
+    __device__ __forceinline__ int ktaps() const { return 1; }
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
+    __device__ __forceinline__ void tile_init(int m0, int M, unsigned char*, int quad, int lane, int4* meta) {
+        const int p = m0 + quad * 32 + lane;
+        int pix = 0;
+        unsigned vmask = 0;
+        if (p < M) {
+            const int n = p / (OH * OW);
+            const int r = p - n * (OH * OW);
+            const int oy = (r / OW) * stride, ox = (r - (r / OW) * OW) * stride;
+            pix = (n * H + oy) * W + ox;
+            unsigned bit = 1u;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx, bit <<= 1) {
+                    const int iy = oy - 1 + ky, ix = ox - 1 + kx;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) vmask |= bit;
+                }
+        }
+        meta[lane] = make_int4(pix, (int)vmask, 0, 0);
+        __syncwarp();
+    }
+    __device__ __forceinline__ void fill(int kb, int, int lane, const int4* meta, float* stage) const {
+        const int tap = 2 * kb + ((lane & 7) >> 2);
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int toff = (ky - 1) * W + (kx - 1);
+        const int ch = (lane & 3) * 4;
+        float4 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int4 m = meta[(lane >> 3) + 4 * j];
+            r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tap < 9 && (((unsigned)m.y >> tap) & 1u)) r[j] = ldg4(src + (size_t)(m.x + toff) * pitch + ch);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stage + ((lane >> 3) + 4 * j) * TS_STAGE_LD + (lane & 7) * 4) = r[j];
+    }
+};
+
 // DCNv2 bilinear gather; K order = (32-channel block, tap, channel).  The corner table of the tile's 128 rows x 9 taps
 // lives in smem (built once per tile by all producers), 20 bytes per (row, tap):
 //   tabB: element offset of the clamped top-left corner (a multiple of 4) | dx | dy << 1   (dx, dy: 1 = the right /
@@ -379,13 +426,22 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
 #pragma unroll
         for (int h = 0; h < LW; h += LH) {
             float v[LH];
-            tmem_ld<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), v);
-#pragma unroll 1
-            for (int q = 1; q < nblk; ++q) {                        // the other partial accumulators, added in a fixed order
-                float v2[LH];
-                tmem_ld<LH>(tmem_acc + (uint32_t)(q * BN) + lane_addr + (uint32_t)(c + h), v2);
+            if (nblk == 2) {                                        // the common case (two issuers): both loads, ONE wait
+                uint32_t r0[LH], r1[LH];
+                tmem_ld_issue<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), r0);
+                tmem_ld_issue<LH>(tmem_acc + (uint32_t)BN + lane_addr + (uint32_t)(c + h), r1);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < LH; ++j) v[j] += v2[j];
+                for (int j = 0; j < LH; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+            } else {
+                tmem_ld<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), v);
+#pragma unroll 1
+                for (int q = 1; q < nblk; ++q) {                    // the other partial accumulators, added in a fixed order
+                    float v2[LH];
+                    tmem_ld<LH>(tmem_acc + (uint32_t)(q * BN) + lane_addr + (uint32_t)(c + h), v2);
+#pragma unroll
+                    for (int j = 0; j < LH; ++j) v[j] += v2[j];
+                }
             }
 #pragma unroll
             for (int q = 0; q < LH / 4; ++q)
@@ -407,7 +463,7 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
         const bool col_ok = col < e.Cout;
         const float4 sc = *reinterpret_cast<const float4*>(ss + (col_ok ? col : 0));
         const float4 sh = *reinterpret_cast<const float4*>(ss + TS_SS_MAXC + (col_ok ? col : 0));
-        constexpr int NJ = 32 / RPI, JB = NJ >= 2 ? 2 : NJ;        // rows of this lane, JB at a time: loads first, then the stores
+        constexpr int NJ = 32 / RPI, JB = NJ >= 4 ? 4 : NJ;        // rows of this lane, JB at a time: loads first, then the stores
 #pragma unroll
         for (int j0 = 0; j0 < NJ; j0 += JB) {
             float4 a[JB], rr[JB];

@@ -59,7 +59,7 @@ class FramePlan:
         M = self.N * out.H * out.W
         w_tc, tc_bn = (None, 0)
         if self.flags & ops.FLAG_TENSORCORE:
-            w_tc, tc_bn = ops.tc_pack(wp, ldw, wp.shape[0], M, taps=kh * kw)
+            w_tc, tc_bn = ops.conv_tc_pack(wp, ldw, sum(s.C for s in srcs), kh, kw, M)
             self._dcn_ws_bytes = max(self._dcn_ws_bytes, lib().deft_tc_scratch_bytes(ldw, wp.shape[0], M, ops.KIND_CONV))
         self.keep += [wp, scale, shift, w_tc]
         self._rec("deft_conv2d_bn_act", ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),

@@ -109,6 +109,16 @@ def tc_pack(wp, ldw, K, M, kind=KIND_CONV, taps=1):
     return blob, bn
 
 
+def conv_tc_pack(wp, ldw, cin_total, kh, kw, M):
+    """tcgen05 weight image of a conv whose packed weight is wp [(ky,kx,ci)][ldw].  The 16-channel 3x3 layers use the
+    tap-major pseudo-channel producer (TsC16AP): their image is packed from a copy zero-padded to K = 192 with taps = 1."""
+    if cin_total == 16 and kh == 3 and kw == 3:
+        pad = torch.zeros((192, wp.shape[1]), dtype=wp.dtype, device=wp.device)
+        pad[: wp.shape[0]] = wp
+        return tc_pack(pad, ldw, 192, M, taps=1)
+    return tc_pack(wp, ldw, wp.shape[0], M, taps=kh * kw)
+
+
 def tc_scratch(ldw, K, M, kind, device):
     n = lib().deft_tc_scratch_bytes(ldw, K, M, kind)
     return torch.empty(n, dtype=torch.uint8, device=device) if n else None
@@ -125,7 +135,7 @@ def conv2d_bn_act(srcs, wp, ldw, scale, shift, cout, kh, kw, stride, pad, relu, 
     fl = flags | (FLAG_RELU if relu else 0)
     if (flags & FLAG_TENSORCORE) and w_tc is None:
         M = s0.N * OH * OW
-        w_tc, tc_bn = tc_pack(wp, ldw, wp.shape[0], M, taps=kh * kw)
+        w_tc, tc_bn = conv_tc_pack(wp, ldw, sum(s.C for s in srcs), kh, kw, M)
         if ws is None:
             ws = tc_scratch(ldw, wp.shape[0], M, KIND_CONV, s0.t.device)
     check(lib().deft_conv2d_bn_act(ptr_array([s.ptr for s in srcs]), int_array([s.C for s in srcs]),
