@@ -479,3 +479,27 @@ def test_odd_kblock_count_many_tiles_per_cta_is_stable(dev):
     r1 = ops.conv2d_bn_act([x], wp1, ldw1, sc1, sh1, 48, 1, 1, 1, 0, False, flags=0).nchw_view()
     y1 = ops.conv2d_bn_act([x], wp1, ldw1, sc1, sh1, 48, 1, 1, 1, 0, False, flags=2).nchw_view()
     assert nerr(y1.cpu(), r1.cpu()) < 1e-5
+
+
+def test_model_on_second_gpu_while_first_is_current():
+    """kernels must launch on a stream of the device that owns their pointers, and the per-kernel shared
+    memory attribute is a per-device property.  A model on cuda:1 driven while cuda:0 is the current device must give the
+    same bits as the same model on cuda:0 (needs 2 GPUs: runs in the 2-GPU gpurun call, skipped elsewhere)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    heads = spec.MOT_HEADS
+    x = spec.make_input((1, 3, 96, 160), tag="twogpu")
+    outs = []
+    torch.cuda.set_device(0)
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        m, sd, opt = build(heads, "mot", dev)
+        out, fm = m(x.to(dev))                                   # current device stays cuda:0 for both
+        emb = m.AFE.forward_feature_extracter(fm, spec.make_uniform((1, 6, 1, 1, 2), -1, 1, tag="twogpu_c").to(dev))
+        aff = m.AFE.forward_stacker_features(emb, emb, False)
+        torch.cuda.synchronize(dev)
+        outs.append(({k: v.cpu() for k, v in out[0].items()}, emb.cpu(), aff))
+        assert torch.cuda.current_device() == 0
+    for k in outs[0][0]:
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+    assert torch.equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
