@@ -23,6 +23,8 @@ _SIGS = {
     "deft_launch_count": (C.c_ulonglong, []),
     "deft_set_pdl": (None, [C.c_int]),
     "deft_simt_fallback_count": (C.c_ulonglong, []),
+    "deft_dcn_patch_launch_count": (C.c_ulonglong, []),
+    "deft_debug_set_dcn_patch": (None, [C.c_int]),
     "deft_debug_set_engine_log": (None, [C.c_int]),
     "deft_debug_set_trace": (None, [c_fp]),
     "deft_get_pdl": (C.c_int, []),

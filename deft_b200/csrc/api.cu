@@ -26,6 +26,19 @@ bool pdl_enabled() {
 static long long* g_trace = nullptr;
 long long* debug_trace_ptr() { return __atomic_load_n(&g_trace, __ATOMIC_RELAXED); }
 static unsigned long long g_fallbacks = 0;
+static unsigned long long g_dcn_patch = 0;
+void note_dcn_patch_launch() { __atomic_fetch_add(&g_dcn_patch, 1ull, __ATOMIC_RELAXED); }
+static int g_dcn_patch_mode = -1;
+int dcn_patch_mode() {
+    int v = __atomic_load_n(&g_dcn_patch_mode, __ATOMIC_RELAXED);
+    if (v < 0) {
+        const char* e = getenv("DEFT_DCN_PATCH");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+        __atomic_store_n(&g_dcn_patch_mode, v, __ATOMIC_RELAXED);
+    }
+    return v;
+}
 static int g_engine_log = -1;
 void note_simt_fallback(const char* op, const char* fmt, ...) {
     __atomic_fetch_add(&g_fallbacks, 1ull, __ATOMIC_RELAXED);
@@ -48,6 +61,8 @@ void note_simt_fallback(const char* op, const char* fmt, ...) {
 extern "C" {
 void deft_debug_set_trace(void* device_buffer) { __atomic_store_n(&deft::g_trace, reinterpret_cast<long long*>(device_buffer), __ATOMIC_RELAXED); }
 void deft_debug_set_engine_log(int enabled) { __atomic_store_n(&deft::g_engine_log, enabled ? 1 : 0, __ATOMIC_RELAXED); }
+void deft_debug_set_dcn_patch(int mode) { __atomic_store_n(&deft::g_dcn_patch_mode, (mode < 0 || mode > 2) ? 0 : mode, __ATOMIC_RELAXED); }
+unsigned long long deft_dcn_patch_launch_count(void) { return __atomic_load_n(&deft::g_dcn_patch, __ATOMIC_RELAXED); }
 unsigned long long deft_simt_fallback_count(void) { return __atomic_load_n(&deft::g_fallbacks, __ATOMIC_RELAXED); }
 unsigned long long deft_launch_count(void) { return __atomic_load_n(&deft::g_launches, __ATOMIC_RELAXED); }
 void deft_set_pdl(int enabled) {

@@ -77,6 +77,8 @@ long long* debug_trace_ptr();  // api.cu: deft_debug_set_trace(); nullptr unless
 // engine: correct, but ~7x slower.  Every such fallback is counted (deft_simt_fallback_count) and, with
 // DEFT_DEBUG_ENGINE=1 / deft_debug_set_engine_log(1), reported on stderr, so a shape regression cannot hide.
 void note_simt_fallback(const char* op, const char* detail_fmt, ...);
+void note_dcn_patch_launch();  // api.cu: deft_dcn_patch_launch_count()
+int dcn_patch_mode();          // api.cu: deft_debug_set_dcn_patch() / DEFT_DCN_PATCH (0 off, 1 on for maps that tile well, 2 on for every map)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};

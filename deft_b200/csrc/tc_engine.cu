@@ -1250,12 +1250,65 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
     return tc_dispatch(t, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
 }
 
+// ---- DCN gather out of a TMA-loaded halo patch (TsDcnPatchAP): 3xFP16 images, N tile 64 or 128, maps that tile into 16x8
+// patches without wasting more than ~15 % of the MMA rows (the 1/4 and 1/8 resolution layers; the deeper ones keep TsDcnAP).
+static int dcn_patch_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
+                              size_t scratch_bytes, cudaStream_t st) {
+    static int why = -1;
+    const int on = dcn_patch_mode();      // default off: measured slower than the global gather (profiles/r2_dcn_patch_experiment.md)
+    if (why < 0) { const char* e = getenv("DEFT_DEBUG_ENGINE"); why = e ? atoi(e) : 0; }
+#define DP_DECLINE(reason) do { if (why) fprintf(stderr, "deft_b200: halo-patch DCN kernel declined (%s): Cin=%d ldw=%d bn=%d %dx%d\n", reason, ap.Cin, ldw, bn, ap.H, ap.W); return DEFT_EINVAL; } while (0)
+    if (!on) return DEFT_EINVAL;
+    if (blob == nullptr || (bn != 64 && bn != 128) || ldw % bn != 0 || ep.Cout % 4 != 0 || ldw > TS_SS_MAXC) DP_DECLINE("tile shape");
+    if (!tc_blob_is_f16(K, 9, bn) || (flags & DEFT_FLAG_TF32X1) || K != 9 * ap.Cin || ap.Cin % 64 != 0) DP_DECLINE("not a 3xFP16 image");
+    if (ap.pitch % 4 != 0 || (reinterpret_cast<uintptr_t>(ap.x) & 15) != 0) DP_DECLINE("alignment");
+    const long long rows = (long long)ceil_div(ap.W, TP_PW) * ceil_div(ap.H, TP_PH) * TC_BM;
+    if (on != 2 && rows * 100 > (long long)ap.H * ap.W * 115) DP_DECLINE("map wastes > 15 % of the patch rows");      // DEFT_DCN_PATCH=2: any map (tests)
+    TmapEncodeFn enc = tmap_encoder();
+    if (enc == nullptr) DP_DECLINE("no cuTensorMapEncodeTiled");
+    TsDcnPatchAP t{};
+    t.H = ap.H; t.W = ap.W; t.x = ap.x; t.pitch = ap.pitch; t.om = ap.om;
+    t.tiles_x = ceil_div(ap.W, TP_PW);
+    t.tiles_y = ceil_div(ap.H, TP_PH);
+    const cuuint64_t gdim[4] = {(cuuint64_t)ap.Cin, (cuuint64_t)ap.W, (cuuint64_t)ap.H, (cuuint64_t)ap.N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ap.pitch * 4, (cuuint64_t)ap.W * ap.pitch * 4, (cuuint64_t)ap.H * ap.W * ap.pitch * 4};
+    const cuuint32_t box[4] = {TC_BK, DP_HW, DP_HH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult enc_rc = enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ap.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (enc_rc != CUDA_SUCCESS) {
+        if (why) fprintf(stderr, "deft_b200: cuTensorMapEncodeTiled -> %d\n", (int)enc_rc);
+        DP_DECLINE("tensor map encode failed");
+    }
+    const int nkb = K / 64, nt = ldw / bn, ncb = ap.Cin / 64;
+    const int m_tiles = ap.N * t.tiles_x * t.tiles_y;
+    int splits = tc_pick_splits(m_tiles * nt, nkb);
+    if (splits > ncb) splits = ncb;
+    if (splits > 1) splits = ceil_div(ncb, ceil_div(ncb, splits));     // whole channel blocks per split
+    if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
+    EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
+    int rc = bn == 64 ? ts_launch<TsDcnPatchAP, 64, 6>(t, blob, nkb, M, nt, splits, epi, st, m_tiles)
+                      : ts_launch<TsDcnPatchAP, 128, 6>(t, blob, nkb, M, nt, splits, epi, st, m_tiles);
+    if (rc == DEFT_EINVAL && why) fprintf(stderr, "deft_b200: halo-patch DCN kernel: launcher declined (bn=%d)\n", bn);
+#undef DP_DECLINE
+    if (rc == DEFT_OK) note_dcn_patch_launch();
+    if (rc != DEFT_OK || splits == 1) return rc;
+    size_t total = (size_t)M * (ep.Cout / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > TC_NUM_SMS * 8) blocks = TC_NUM_SMS * 8;
+    launch_pdl(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const float*>(scratch), splits, M, ldw, ep);
+    DEFT_CHECK_LAUNCH("splitk_reduce");
+    return DEFT_OK;
+}
+
 int tc_dcn_dispatch(const DcnAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                     size_t scratch_bytes, cudaStream_t st) {
     if (ap.Cin % 32 != 0 || bn > 128) return DEFT_EINVAL;
     static int ts_dcn = -1;
     if (ts_dcn < 0) { const char* e = getenv("DEFT_TC_TS_DCN"); ts_dcn = e ? atoi(e) : 1; }
     if (ts_dcn && ts_enabled() && (long long)M * ap.pitch < 2147483647LL) {
+        const int rc_patch = dcn_patch_dispatch(ap, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st);
+        if (rc_patch != DEFT_EINVAL) return rc_patch;
         TsDcnAP d{};
         d.a = ap;
         return ts_dispatch(d, blob, bn, ldw, K, M, ep, flags, scratch, scratch_bytes, st, 9);

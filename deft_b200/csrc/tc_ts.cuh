@@ -332,6 +332,8 @@ constexpr int TP_STAGE_BYTES = (TP_BOX_BYTES + 1023) / 1024 * 1024;   // ring st
 constexpr int TP_MAX_STAGES = 4;
 struct TsPatchAP {
     static constexpr bool kPatch = true;
+    static constexpr bool kDcn = false;
+    static constexpr int kHW = TP_HW, kHH = TP_HH, kHalo = 1, kBoxBytes = TP_BOX_BYTES, kStageBytes = TP_STAGE_BYTES;
     static constexpr int kExtraSmemBytes = 0;
     alignas(64) CUtensorMap tmap;                                  // dims {C, W, H, N} of the NHWC source
     int H, W, tiles_x, tiles_y;
@@ -340,6 +342,45 @@ struct TsPatchAP {
     __device__ __forceinline__ void setup_once(unsigned char*) {}
     __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
     __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
+};
+
+// DCNv2 gather out of a halo patch (round 2).  The global-memory gather (TsDcnAP above) is bound by the latency of its
+// corner loads: 4 serial rounds of 8 LDG.128 per lane and k-block, nearly every round containing an L1 miss (the 100 KB
+// neighbourhood of a 128-pixel row tile does not fit the ~50 KB of L1 left beside the operand rings).  Here an M tile is
+// a 16 x 8 pixel patch as in TsPatchAP, and ONE TMA tensor copy per 32-channel block lands the (16+2+2R) x (8+2+2R) halo
+// in shared memory (R = DP_R pixels of margin for the learned offsets).  Producer thread = output pixel: it recomputes
+// its sampling position from the offset/mask row (3 cached loads per tap; no corner table, no table-build barrier),
+// reads the four corners with LDS.128 (the TMA swizzle keeps neighbouring pixels on different banks), blends, splits and
+// tcgen05.st's -- no transposition stage either.  A corner pair that leaves the halo (|offset| >= R) falls back to the
+// global loads of the old path for that pixel and tap: any offset is handled, small ones are fast.
+constexpr int DP_R = 1;
+constexpr int DP_HW = TP_PW + 2 + 2 * DP_R, DP_HH = TP_PH + 2 + 2 * DP_R;       // 20 x 12
+constexpr int DP_BOX_BYTES = DP_HW * DP_HH * 128;                               // 30720
+constexpr int DP_STAGE_BYTES = (DP_BOX_BYTES + 1023) / 1024 * 1024;
+struct TsDcnPatchAP {
+    static constexpr bool kPatch = true;
+    static constexpr bool kDcn = true;
+    static constexpr int kHW = DP_HW, kHH = DP_HH, kHalo = 1 + DP_R, kBoxBytes = DP_BOX_BYTES, kStageBytes = DP_STAGE_BYTES;
+    static constexpr int kExtraSmemBytes = 0;
+    alignas(64) CUtensorMap tmap;                                  // dims {C, W, H, N} of the NHWC input
+    int H, W, tiles_x, tiles_y;
+    const float* x;                                                // the same input through plain pointers (out-of-halo corners)
+    int pitch;
+    const float* om;                                               // [P, 32] offsets (2k = dy, 2k+1 = dx) and mask logits (18 + k)
+    __device__ __forceinline__ int ktaps() const { return 9; }
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
+    __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
+    __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
+};
+template <class AP, bool P = AP::kPatch>
+struct TsPG {                                                      // patch geometry of an A producer (none for the gather producers)
+    static constexpr bool DCN = false;
+    static constexpr int HW = 1, HALO = 0, BOX = 0, STAGE = 0;
+};
+template <class AP>
+struct TsPG<AP, true> {
+    static constexpr bool DCN = AP::kDcn;
+    static constexpr int HW = AP::kHW, HALO = AP::kHalo, BOX = AP::kBoxBytes, STAGE = AP::kStageBytes;
 };
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
@@ -357,6 +398,13 @@ constexpr int TS_KGROUPS = TC_PWARPS / 4;       // k-block interleave across pro
 // which the two issuers' MMAs land is timing dependent and results stop being bit-identical run to run
 // (tests/test_gpu_frame.py::test_c2_full_size_properties caught exactly that).
 constexpr int TS_ISSUERS = 2;
+#ifndef DEFT_TS_SETMAXNREG
+#define DEFT_TS_SETMAXNREG 0  // tried in r2: ptxas keeps the producers' spill count and the 56-register epilogue gains 60 reloads; off
+#endif
+// 16 producer warps x 32 x (96 - 80) = 8192 registers taken = 4 x 32 x (80 - 56) + 4 x 32 x (80 - 40) released
+#define DEFT_TS_PROD_REGS 96
+#define DEFT_TS_EPI_REGS 56
+#define DEFT_TS_AUX_REGS 40
 #ifndef DEFT_TS_PAIR32
 #define DEFT_TS_PAIR32 0     // 1 = the N = 32 instantiation issues [hi|lo] as one N = 64 MMA (see TsCfg::PAIR); measured neutral in r2 (producer-bound), off
 #endif
@@ -391,7 +439,6 @@ struct TsCfg {
     static constexpr int SA = SA_RAW > 6 ? 6 : SA_RAW;                  // A ring depth
     static constexpr int B_TILE = BN * 128;
     static constexpr int B_STAGE = PASSES == 3 ? 2 * B_TILE : B_TILE;
-    static constexpr int P_STAGE = F16 ? 2 * TP_STAGE_BYTES : TP_STAGE_BYTES;   // halo patch of one k-block's channels
 };
 
 // Accumulator tile -> output, 32 (or BN) columns at a time.  tcgen05.ld hands every lane one accumulator ROW; storing
@@ -498,6 +545,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     using Cfg = TsCfg<BN, NPASS>;
     constexpr int SA = Cfg::SA;
     constexpr bool kPatch = AP::kPatch;
+    using PG = TsPG<AP>;
+    constexpr int P_SUB = PG::STAGE;                               // one 32-channel halo patch
+    constexpr int P_STAGE = Cfg::F16 ? 2 * P_SUB : P_SUB;          // halo patch of one k-block's channels
     // the gather producers keep per-thread state in their AP (private copy); the patch AP holds the TMA descriptor,
     // which must stay in param space
     typename std::conditional<kPatch, const AP&, AP>::type ap = ap_param;
@@ -507,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     unsigned char* smem = smem_raw + pad;
     // layout: [patch ring: ps x TP_STAGE_BYTES (patch producer only)] [sb x B_STAGE] [barriers + tmem slot: 512 B] [epilogue stages]
     //         [producer stages (gather producers only)] [AP extra]
-    const uint32_t patch_bytes = kPatch ? (uint32_t)ps * Cfg::P_STAGE : 0u;
+    const uint32_t patch_bytes = kPatch ? (uint32_t)ps * P_STAGE : 0u;
     const uint32_t sbase = raw_addr + pad + patch_bytes;  // weight ring
     const uint32_t bar_base = sbase + (uint32_t)sb * Cfg::B_STAGE;
     auto a_full = [&](int s) { return bar_base + 8u * s; };
@@ -560,10 +610,150 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     const int tiles_mn = ts.m_tiles * ts.n_tiles;
     pdl_launch_dependents();                              // the next launch may take SMs as our CTAs retire
 
+    // Register rebalancing between the warpgroups (setmaxnreg): the kernel launches with 80 registers per thread
+    // (768 threads x 80 = 60 K of the 64 K file), which the A producers overflow -- their spills go through an L1 that the
+    // ~200 KB shared-memory carve-out leaves ~30 KB of, i.e. every spill reload is an L2 round trip in the hot loop.  The
+    // issuer / copy warpgroup needs a few dozen registers and the epilogue warpgroup ~64: they release theirs, the four
+    // producer warpgroups take them.  (Warpgroup = 4 consecutive warps; every warp of one executes the same setmaxnreg.)
+#if DEFT_TS_SETMAXNREG
+    if (warp < TC_PWARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DEFT_TS_PROD_REGS));
+    else if (warp < TC_MMA_WARP) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DEFT_TS_EPI_REGS));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DEFT_TS_AUX_REGS));
+#endif
+
     if (warp < TC_PWARPS) {
         // ===================== A producers: warp = (TMEM lane quadrant, k-group) =====================
         pdl_wait();                                       // activations (and the DCN offset map) come from the predecessor
-        if constexpr (kPatch) {
+        if constexpr (kPatch && PG::DCN) {
+            // ----- DCN patch producer (3xFP16 only): thread = output pixel; bilinear corners out of the halo patch
+            static_assert(!PG::DCN || Cfg::F16, "the DCN patch producer is written for 64-channel (3xFP16) k-blocks");
+            const int quad = warp & 3, grp = warp >> 2;
+            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+            const int r = quad * 32 + lane, ry = r >> 4, rx = r & 15;
+            const int H = ap.H, W = ap.W, pitch = ap.pitch, rowpitch = W * pitch;
+            const int per_img = ap.tiles_x * ap.tiles_y;
+            int gk0 = 0, gc0 = 0;
+            for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
+                const int z = t / tiles_mn, mn = t - z * tiles_mn;
+                const int mt = mn / ts.n_tiles;
+                const int n = mt / per_img, tr = mt - n * per_img;
+                const int ty0 = (tr / ap.tiles_x) * TP_PH, tx0 = (tr % ap.tiles_x) * TP_PW;
+                const int y = ty0 + ry, xx = tx0 + rx;
+                const bool pix_ok = y < H && xx < W;
+                const float* omrow = ap.om + ((size_t)(n * H + (pix_ok ? y : 0)) * W + (pix_ok ? xx : 0)) * 32;
+                const int hy0 = ty0 - PG::HALO, hx0 = tx0 - PG::HALO;                   // image coordinates of halo element (0, 0)
+                const int kb0 = z * ts.kb_per_split;
+                const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;      // whole channel blocks: multiple of 9
+                const int c64_0 = kb0 / 9;
+                int last_c = -1;
+                const float* pbase = nullptr;
+                int i = (grp - (gk0 % TS_KGROUPS) + TS_KGROUPS) % TS_KGROUPS;
+                for (; i < nkb; i += TS_KGROUPS) {
+                    const int c = i / 9, tap = i - c * 9;
+                    if (tid == grp * 128) TC_TRACE(1, gk0 + i, 0);
+                    // sampling position of this pixel and tap (dcn_v2: zero outside (-1, H) x (-1, W), per-corner bounds)
+                    float u00 = 0.f, u01 = 0.f, u10 = 0.f, u11 = 0.f;
+                    int pidx = 0, dxs = 0, dys = 0;                                  // patch index of the top-left corner, strides to the others
+                    const float* gp = nullptr;                                       // != nullptr: corners leave the halo, read them from global
+                    int gdx = 0, gdy = 0;
+                    if (pix_ok) {
+                        const float dy = __ldg(omrow + 2 * tap), dx = __ldg(omrow + 2 * tap + 1);
+                        const float mk = sigmoidf_(__ldg(omrow + 18 + tap));
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const float py = (float)(y - 1 + ky) + dy, px = (float)(xx - 1 + kx) + dx;
+                        if (py > -1.f && py < (float)H && px > -1.f && px < (float)W) {
+                            const float fy = floorf(py), fx = floorf(px);
+                            const int y0 = (int)fy, x0 = (int)fx;
+                            const float ly = py - fy, lx = px - fx, hy = 1.f - ly, hx = 1.f - lx;
+                            const bool y0ok = y0 >= 0, y1ok = y0 + 1 <= H - 1, x0ok = x0 >= 0, x1ok = x0 + 1 <= W - 1;
+                            const float wy0 = y0ok ? hy : 0.f, wy1 = y1ok ? ly : 0.f, wx0 = x0ok ? hx * mk : 0.f, wx1 = x1ok ? lx * mk : 0.f;
+                            u00 = wy0 * wx0; u01 = wy0 * wx1; u10 = wy1 * wx0; u11 = wy1 * wx1;
+                            const int yc = y0ok ? y0 : 0, xc = x0ok ? x0 : 0;         // y0 = -1: the lower row IS row 0 (its weight sits in u1x)
+                            const int ex = (x0ok && x1ok) ? 1 : 0, ey = (y0ok && y1ok) ? 1 : 0;
+                            const int cy = yc - hy0, cx = xc - hx0;
+                            if (cy >= 0 && cx >= 0 && cy + ey < AP::kHH && cx + ex < PG::HW) {
+                                pidx = cy * PG::HW + cx; dxs = ex; dys = ey * PG::HW;
+                            } else {
+                                gp = ap.x + (size_t)((n * H + yc) * W + xc) * pitch;
+                                gdx = ex ? pitch : 0; gdy = ey ? rowpitch : 0;
+                            }
+                        }
+                    }
+                    if (c != last_c) {
+                        if (last_c >= 0) {                 // done with the previous channel block's patch
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
+                        }
+                        const int gc = gc0 + c;
+                        mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
+                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * P_STAGE);
+                        last_c = c;
+                    }
+                    const int gk = gk0 + i;
+                    const int sa = gk % SA;
+                    const uint32_t pa = (uint32_t)(gk / SA) & 1u;
+                    const uint32_t acol = tmem_base + lane_addr + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
+                    const int i00 = pidx, i01 = pidx + dxs, i10 = pidx + dys, i11 = pidx + dys + dxs;
+                    const float* gx = gp != nullptr ? gp + (size_t)(c64_0 + c) * 64 : nullptr;
+                    float4 x[8];
+                    auto blend32 = [&](int h) {            // 32 channels (half h of the k-block) of this pixel's sample -> x[0..7]
+                        if (gx == nullptr) {
+                            const float* ph = pbase + h * (P_SUB / 4);
+                            const float* q00 = ph + i00 * 32; const float* q01 = ph + i01 * 32;
+                            const float* q10 = ph + i10 * 32; const float* q11 = ph + i11 * 32;
+                            const int s00 = i00 & 7, s01 = i01 & 7, s10 = i10 & 7, s11 = i11 & 7;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 a0 = *reinterpret_cast<const float4*>(q00 + ((q ^ s00) << 2));
+                                const float4 a1 = *reinterpret_cast<const float4*>(q01 + ((q ^ s01) << 2));
+                                const float4 a2 = *reinterpret_cast<const float4*>(q10 + ((q ^ s10) << 2));
+                                const float4 a3 = *reinterpret_cast<const float4*>(q11 + ((q ^ s11) << 2));
+                                x[q].x = u00 * a0.x + u01 * a1.x + u10 * a2.x + u11 * a3.x; x[q].y = u00 * a0.y + u01 * a1.y + u10 * a2.y + u11 * a3.y;
+                                x[q].z = u00 * a0.z + u01 * a1.z + u10 * a2.z + u11 * a3.z; x[q].w = u00 * a0.w + u01 * a1.w + u10 * a2.w + u11 * a3.w;
+                            }
+                        } else {
+                            const float* g = gx + h * 32;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 a0 = ldg4(g + q * 4), a1 = ldg4(g + gdx + q * 4), a2 = ldg4(g + gdy + q * 4), a3 = ldg4(g + gdy + gdx + q * 4);
+                                x[q].x = u00 * a0.x + u01 * a1.x + u10 * a2.x + u11 * a3.x; x[q].y = u00 * a0.y + u01 * a1.y + u10 * a2.y + u11 * a3.y;
+                                x[q].z = u00 * a0.z + u01 * a1.z + u10 * a2.z + u11 * a3.z; x[q].w = u00 * a0.w + u01 * a1.w + u10 * a2.w + u11 * a3.w;
+                            }
+                        }
+                    };
+                    blend32(0);
+                    if (tid == grp * 128) TC_TRACE(1, gk, 1);
+                    mbar_wait(a_empty(sa), pa ^ 1u, 2, gk, quad == 0 ? prog : nullptr, grp);
+                    __syncwarp();                              // converged before the .aligned tcgen05.st
+                    tc_fence_after();
+                    if (tid == grp * 128) TC_TRACE(1, gk, 2);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1) { blend32(1); __syncwarp(); }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const float v[16] = {x[4 * q].x, x[4 * q].y, x[4 * q].z, x[4 * q].w, x[4 * q + 1].x, x[4 * q + 1].y, x[4 * q + 1].z, x[4 * q + 1].w,
+                                                 x[4 * q + 2].x, x[4 * q + 2].y, x[4 * q + 2].z, x[4 * q + 2].w, x[4 * q + 3].x, x[4 * q + 3].y, x[4 * q + 3].z, x[4 * q + 3].w};
+                            uint32_t hi[8], lo[8];
+                            split_f16x3(v, hi, lo);
+                            tmem_st8u(acol + (uint32_t)(h * 16 + q * 8), hi);
+                            tmem_st8u(acol + 32u + (uint32_t)(h * 16 + q * 8), lo);
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full(sa));
+                    if (tid == grp * 128) TC_TRACE(1, gk, 3);
+                }
+                if (last_c >= 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
+                }
+                gk0 += nkb;
+                gc0 += nkb / 9;
+            }
+        } else if constexpr (kPatch) {
             // ----- patch producer: thread = output pixel (ry, rx) of the 16x8 patch, operands from the TMA-filled halo patch
             const int quad = warp & 3, grp = warp >> 2;
             const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -586,7 +776,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                         }
                         const int gc = gc0 + c;
                         mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
-                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * Cfg::P_STAGE);
+                        pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * P_STAGE);
                         last_c = c;
                     }
                     const int gk = gk0 + i;
@@ -615,7 +805,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             if (h == 1) {
-                                const float* prow1 = prow + TP_STAGE_BYTES / 4;
+                                const float* prow1 = prow + P_SUB / 4;
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow1 + ((q ^ sw) << 2));
                             }
@@ -906,7 +1096,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int z = t / tiles_mn, mn = t - z * tiles_mn;
                 const int mt = mn / ts.n_tiles;
                 const int n = mt / per_img, tr = mt - n * per_img;
-                const int y0 = (tr / ap.tiles_x) * TP_PH - 1, x0 = (tr % ap.tiles_x) * TP_PW - 1;
+                const int y0 = (tr / ap.tiles_x) * TP_PH - PG::HALO, x0 = (tr % ap.tiles_x) * TP_PW - PG::HALO;
                 const int kb0 = z * ts.kb_per_split;
                 const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
                 const int c0 = kb0 / 9, nch = nkb / 9;
@@ -915,12 +1105,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc, prog, 8);
                     if (elect_one_sync()) {
                         if constexpr (Cfg::F16) {          // 64 channels per k-block: two 32-channel boxes into the two halves of the stage
-                            mbar_arrive_expect_tx(p_full(s), (uint32_t)(2 * TP_BOX_BYTES));
-                            tma_load_4d(raw_addr + pad + (uint32_t)s * Cfg::P_STAGE, &ap_param.tmap, (c0 + c) * 64, x0, y0, n, p_full(s));
-                            tma_load_4d(raw_addr + pad + (uint32_t)s * Cfg::P_STAGE + TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * 64 + 32, x0, y0, n, p_full(s));
+                            mbar_arrive_expect_tx(p_full(s), (uint32_t)(2 * PG::BOX));
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE, &ap_param.tmap, (c0 + c) * 64, x0, y0, n, p_full(s));
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE + P_SUB, &ap_param.tmap, (c0 + c) * 64 + 32, x0, y0, n, p_full(s));
                         } else {
-                            mbar_arrive_expect_tx(p_full(s), (uint32_t)TP_BOX_BYTES);
-                            tma_load_4d(raw_addr + pad + (uint32_t)s * TP_STAGE_BYTES, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
+                            mbar_arrive_expect_tx(p_full(s), (uint32_t)PG::BOX);
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE, &ap_param.tmap, (c0 + c) * TC_BK, x0, y0, n, p_full(s));
                         }
                     }
                     __syncwarp();
@@ -944,7 +1134,8 @@ template <class AP, int BN, int NPASS>
 static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st, int m_tiles_override = 0) {
     using Cfg = TsCfg<BN, NPASS>;
     constexpr int ps = AP::kPatch ? (Cfg::F16 ? 2 : TP_MAX_STAGES) : 0;
-    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * Cfg::P_STAGE : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
+    constexpr int P_STAGE = (Cfg::F16 ? 2 : 1) * TsPG<AP>::STAGE;
+    const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * P_STAGE : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
     if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, 9) * 9;      // whole channel blocks per split

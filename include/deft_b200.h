@@ -63,6 +63,12 @@ int deft_get_pdl(void);
  * 4*96*4 int64 into which CTA 0 of the tcgen05 kernels stamps clock64() per protocol point (tools/tc_trace.py);
  * NULL disarms it. */
 unsigned long long deft_simt_fallback_count(void);
+/* The second DCN gather kernel (TsDcnPatchAP: bilinear corners out of a TMA-loaded halo patch in shared memory).  Built and
+ * parity-tested in round 2, measured slower than the global gather (profiles/r2_dcn_patch_experiment.md), so it is OFF unless
+ * DEFT_DCN_PATCH / deft_debug_set_dcn_patch says otherwise: 0 off, 1 on for maps that tile into 16x8 patches, 2 on for every
+ * map.  deft_dcn_patch_launch_count(): gather-GEMM launches that took it since load (lets a test prove which kernel ran). */
+void deft_debug_set_dcn_patch(int mode);
+unsigned long long deft_dcn_patch_launch_count(void);
 void deft_debug_set_engine_log(int enabled);
 void deft_debug_set_trace(void* device_buffer);
 

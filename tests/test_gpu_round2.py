@@ -481,6 +481,54 @@ def test_odd_kblock_count_many_tiles_per_cta_is_stable(dev):
     assert nerr(y1.cpu(), r1.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("chi,cho,h,w,n,off_scale", [
+    (64, 64, 24, 48, 1, 1.0),        # whole 16x8 patches, offsets within the halo margin: the LDS path
+    (64, 64, 40, 46, 2, 3.0),        # partial patches on both edges, two images, offsets that leave the halo AND the image
+    (128, 128, 32, 32, 1, 1.0),      # N tile 128, two 64-channel blocks per tile
+    (128, 64, 16, 48, 2, 3.0),
+    (256, 256, 16, 32, 1, 1.0),      # few tiles: split-K over whole channel blocks + two N tiles
+    (64, 64, 152, 272, 1, 1.0),      # the 1/4-resolution DLA layer at its C2 size: several tiles per CTA
+])
+def test_dcn_halo_patch_kernel_vs_oracle(dev, chi, cho, h, w, n, off_scale):
+    """Round 2 experiment, kept parity-tested: a second DCN gather kernel that reads its corners from a TMA-loaded halo patch in
+    shared memory (TsDcnPatchAP; a corner pair outside the halo falls back to global loads for that pixel and tap).  It
+    measured slower than the global gather and is off by default (deft_debug_set_dcn_patch).  Same oracle and tolerance as
+    test_dcn_all_dla_shapes_vs_oracle; the launch counter proves the patch kernel is the one that ran; the default kernel
+    (global gather through L1) runs the same case beside it."""
+    from deft_b200 import _lib, ops
+    from deft_b200.dcn_v2 import DCN
+    sp = {}
+    spec._deform(sp, "d", chi, cho)
+    sd = spec.make_state_dict(sp, seed=chi + cho + h)
+    sd["d.conv.conv_offset_mask.bias"] = sd["d.conv.conv_offset_mask.bias"] * off_scale
+    if off_scale > 1.0:
+        sd["d.conv.conv_offset_mask.weight"] = sd["d.conv.conv_offset_mask.weight"] * off_scale
+    x = spec.make_input((n, chi, h, w), tag=f"dcnpatch{chi}{cho}{h}")
+    torch.set_num_threads(os.cpu_count() or 8)
+    with torch.no_grad():
+        ref = restate.dcn_forward(sd, "d.conv", x, explicit=False)
+    mod = DCN(chi, cho)
+    mod.load_state_dict({k[len("d.conv."):]: v for k, v in sd.items() if k.startswith("d.conv.")})
+    mod = mod.to(dev)
+    L = _lib.lib()
+    with torch.no_grad():
+        y_gather = mod(x.to(dev), flags=ops.FLAG_TENSORCORE)
+    torch.cuda.synchronize()
+    assert nerr(y_gather.cpu(), ref) < TOL
+    before = L.deft_dcn_patch_launch_count()
+    L.deft_debug_set_dcn_patch(1)
+    try:
+        with torch.no_grad():
+            y = mod(x.to(dev), flags=ops.FLAG_TENSORCORE)
+            y2 = mod(x.to(dev), flags=ops.FLAG_TENSORCORE)
+        torch.cuda.synchronize()
+    finally:
+        L.deft_debug_set_dcn_patch(0)
+    assert L.deft_dcn_patch_launch_count() == before + 2, "the halo-patch DCN kernel did not take this shape"
+    assert torch.equal(y, y2)
+    assert nerr(y.cpu(), ref) < TOL
+
+
 def test_model_on_second_gpu_while_first_is_current():
     """kernels must launch on a stream of the device that owns their pointers, and the per-kernel shared
     memory attribute is a per-device property.  A model on cuda:1 driven while cuda:0 is the current device must give the
