@@ -66,10 +66,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded wait: a protocol bug must trap, never hang the GPU.  After ~0.5 s every stuck warp reports where it waits
 // (site / aux are caller-defined: which barrier of the protocol, which k-block or tile), after ~1.5 s the kernel traps.
+#ifndef DEFT_TS_PROGRESS
+#define DEFT_TS_PROGRESS 1    // 0 = no progress-board store before a wait (A/B builds: what the board costs)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int aux = 0, volatile int* prog = nullptr, int slot = 0) {
     // prog (TS kernel): a per-CTA progress board in shared memory -- every role's leader posts (site << 24 | counter) before it
     // waits, so that a stall report shows where ALL roles of the CTA stand, not only the warp that timed out
+#if DEFT_TS_PROGRESS
     if (prog != nullptr && (threadIdx.x & 31) == 0) prog[slot] = (site << 24) | (aux & 0xffffff);
+#endif
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
     bool reported = false;
@@ -79,6 +84,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int sit
             reported = true;
             if ((threadIdx.x & 31) == 0) {
                 printf("deft tc_engine: mbarrier stall block %d warp %d site %d aux %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, site, aux, bar, parity);
+                if (prog != nullptr)
+                    printf("deft tc_engine: block %d roles (site<<24|count): prod %x %x %x %x | issuer %x %x | bcopy %x | epi %x | tma %x\n", blockIdx.x,
+                           prog[0], prog[1], prog[2], prog[3], prog[4], prog[5], prog[6], prog[7], prog[8]);
+            }
+        }
+        if (dt > 3000000000LL) __trap();
+    }
+}
+// Two barriers at once (the TS issuers: A stage and weight stage of a k-block).  Both try_waits are issued back to back so
+// that their latencies overlap; waited one after the other they cost the issuer ~170 + ~400 cycles per k-block even when both
+// phases had completed long before (r2_trace_conv32: 1715 cycles per own k-block of which 542 issue MMAs).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b, int site_a, int site_b, int aux,
+                                           volatile int* prog, int slot) {
+#if DEFT_TS_PROGRESS
+    if (prog != nullptr && (threadIdx.x & 31) == 0) prog[slot] = (site_a << 24) | (aux & 0xffffff);
+#endif
+    uint32_t oa = mbar_try_wait(bar_a, par_a), ob = mbar_try_wait(bar_b, par_b);
+    if (oa & ob) return;
+    long long t0 = clock64();
+    bool reported = false;
+    while (true) {
+        if (!oa) oa = mbar_try_wait(bar_a, par_a);
+        if (!ob) ob = mbar_try_wait(bar_b, par_b);
+        if (oa & ob) return;
+        const long long dt = clock64() - t0;
+        if (dt > 1000000000LL && !reported) {
+            reported = true;
+            if ((threadIdx.x & 31) == 0) {
+                printf("deft tc_engine: mbarrier stall block %d warp %d site %d aux %d bar %u parity %u\n", blockIdx.x, threadIdx.x >> 5, oa ? site_b : site_a, aux,
+                       oa ? bar_b : bar_a, oa ? par_b : par_a);
                 if (prog != nullptr)
                     printf("deft tc_engine: block %d roles (site<<24|count): prod %x %x %x %x | issuer %x %x | bcopy %x | epi %x | tma %x\n", blockIdx.x,
                            prog[0], prog[1], prog[2], prog[3], prog[4], prog[5], prog[6], prog[7], prog[8]);
@@ -800,10 +835,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_igemm_kernel(AP ap, const fl
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(b * BN);
                 for (int i = 0; i < nkb; ++i, ++gk) {
                     if (lane == 0) TC_TRACE(0, gk, 0);
-                    mbar_wait(full_a(s), ph);
-                    if (lane == 0) TC_TRACE(0, gk, 1);
-                    mbar_wait(full_b(s), ph);
-                    if (lane == 0) TC_TRACE(0, gk, 2);
+                    mbar_wait2(full_a(s), ph, full_b(s), ph, 5, 6, gk, nullptr, 0);     // both operands of the stage, one round trip
+                    if (lane == 0) { TC_TRACE(0, gk, 1); TC_TRACE(0, gk, 2); }
                     tc_fence_after();
                     const uint32_t a_hi = sbase + (uint32_t)s * STAGE_BYTES;
                     const uint32_t a_lo = a_hi + TC_A_TILE;

@@ -405,6 +405,9 @@ constexpr int TS_ISSUERS = 2;
 #define DEFT_TS_PROD_REGS 96
 #define DEFT_TS_EPI_REGS 56
 #define DEFT_TS_AUX_REGS 40
+#ifndef DEFT_TS_CHAINS
+#define DEFT_TS_CHAINS 0      // 1 = several accumulate chains per issuer at N <= 32 (TsCfg::CH): parity-green, measured neutral (the issuer's own waits bound N <= 64), off
+#endif
 #ifndef DEFT_TS_PAIR32
 #define DEFT_TS_PAIR32 0     // 1 = the N = 32 instantiation issues [hi|lo] as one N = 64 MMA (see TsCfg::PAIR); measured neutral in r2 (producer-bound), off
 #endif
@@ -431,8 +434,16 @@ struct TsCfg {
     // are contiguous and form a valid 64-row swizzled tile): 2 MMAs per k-step instead of 3.  The accumulator of an
     // issuer is then 2 x BN columns ([hi*hi + lo*hi | hi*lo]) and the epilogue adds the column blocks.
     static constexpr bool PAIR = (BN == 32 && NPASS == 3 && DEFT_TS_PAIR32);
-    static constexpr int ACCW = PAIR ? 2 * BN : BN;                     // accumulator columns of one issuer
-    static constexpr int NBLK = (PAIR ? 2 : 1);                         // BN-wide column blocks per issuer
+    // Accumulate chains per issuer (3xFP16, narrow tiles).  A tcgen05.mma into an accumulator that the previous MMA is still
+    // updating waits for it: 96.8 cycles per MMA whatever N is (profiles/r2_engine_experiments.md section 5), so at N <= 32 --
+    // where the MMA itself takes 8-16 cycles -- the two issuers' two chains cap a k-block at 12 x 97 / 2 = 581 cycles while the
+    // producers need ~330.  The k-steps of a k-block therefore rotate over CH accumulators per issuer (N = 32: 2, N = 16: 4;
+    // the accumulator columns are there: 2 sets x 2 issuers x CH x BN = 256); the epilogue adds the ISS x CH partial tiles in a
+    // fixed order.  Measured (r2, tools/gpu_call16.sh): tests green, frame 593 vs 597 fps -- the N = 32 issuer spends 1715 cycles per
+    // own k-block of which 542 issue MMAs, the rest are its barrier waits and commits, so the chain is not what binds.  Default off.
+    static constexpr int CH = (F16 && DEFT_TS_CHAINS && BN <= 32) ? (BN == 32 ? 2 : 4) : 1;
+    static constexpr int ACCW = PAIR ? 2 * BN : CH * BN;                // accumulator columns of one issuer
+    static constexpr int NBLK = (PAIR ? 2 : CH);                        // BN-wide column blocks per issuer
     static constexpr int NBUF = (2 * ISS * ACCW <= 256) ? 2 : 1;        // accumulator sets (double-buffered across tiles when they fit)
     static constexpr int A0 = NBUF * ISS * ACCW;                        // first A column (after the accumulators)
     static constexpr int SA_RAW = (512 - A0) / ACOLS;
@@ -473,13 +484,21 @@ __device__ __forceinline__ void ts_epilogue(const EpiStd& epi, uint32_t tmem_acc
 #pragma unroll
         for (int h = 0; h < LW; h += LH) {
             float v[LH];
-            if (nblk == 2) {                                        // the common case (two issuers): both loads, ONE wait
-                uint32_t r0[LH], r1[LH];
-                tmem_ld_issue<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), r0);
-                tmem_ld_issue<LH>(tmem_acc + (uint32_t)BN + lane_addr + (uint32_t)(c + h), r1);
-                tmem_ld_wait();
+            if ((nblk & 1) == 0) {                                  // the common case (two issuers [x chains]): two loads per wait
+#pragma unroll 1
+                for (int q = 0; q < nblk; q += 2) {
+                    uint32_t r0[LH], r1[LH];
+                    tmem_ld_issue<LH>(tmem_acc + (uint32_t)(q * BN) + lane_addr + (uint32_t)(c + h), r0);
+                    tmem_ld_issue<LH>(tmem_acc + (uint32_t)((q + 1) * BN) + lane_addr + (uint32_t)(c + h), r1);
+                    tmem_ld_wait();
+                    if (q == 0) {
 #pragma unroll
-                for (int j = 0; j < LH; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                        for (int j = 0; j < LH; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < LH; ++j) v[j] = (v[j] + __uint_as_float(r0[j])) + __uint_as_float(r1[j]);
+                    }
+                }
             } else {
                 tmem_ld<LH>(tmem_acc + lane_addr + (uint32_t)(c + h), v);
 #pragma unroll 1
@@ -574,9 +593,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     auto p_full = [&](int s) { return bar_base + 8u * (40 + s); };
     auto p_empty = [&](int s) { return bar_base + 8u * (44 + s); };
     const uint32_t tmem_slot = bar_base + 8u * 38;
-    // progress board for stall reports (static shared memory: its address costs no register): see mbar_wait
+    // progress board for stall reports (static shared memory: its address costs no register): see mbar_wait.  Every wait of every
+    // role leader then starts with a shared-memory store, through an LSU the producers keep busy: 0.7 % of the C2 frame rate
+    // (609.1 / 609.6 fps with, 613.5 / 613.8 without, same box).  So the board is armed on request (DEFT_TC_DBG bit 32); a
+    // stall still reports its own site and traps either way -- reproduce with the bit set to see where the other roles stood.
     __shared__ int prog_board[16];
-    volatile int* const prog = prog_board;
+    volatile int* const prog = (dbg & 32) ? prog_board : nullptr;
     unsigned char* epi_stage = smem + patch_bytes + (size_t)sb * Cfg::B_STAGE + 512;     // epilogue warps' transpose stages, scale, shift
     unsigned char* ap_common = epi_stage + TS_EPI_SMEM;                                  // producer warps' transpose stages + row tables
     unsigned char* ap_extra = ap_common + TS_COMMON_SMEM;
@@ -598,7 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             mbar_init(p_full(s), 1);
             mbar_init(p_empty(s), TC_PWARPS);
         }
-        for (int q = 0; q < 16; ++q) prog[q] = 0;
+        for (int q = 0; q < 16; ++q) prog_board[q] = 0;
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -969,7 +991,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             // The tensor core adds every MMA into the fp32 accumulator with round-toward-zero (measured: tools/tc_bias.py, a
             // gain of -1.6e-8 per accumulate step, e.g. -6.8e-6 at K = 2304).  An accumulator of this tile took
             // 4 * NPASS * ceil(nkb / ISS) steps; the expected shrink is undone here (DEFT_TC_RZ_COMP=0 disables it).
-            const float rz_gain = 1.0f + rz_comp * (float)(4 * Cfg::PASSES * ((nkb + Cfg::ISS - 1) / Cfg::ISS));
+            const float rz_gain = 1.0f + rz_comp * (float)((4 / Cfg::CH) * Cfg::PASSES * ((nkb + Cfg::ISS - 1) / Cfg::ISS));
             TsRowMap rm{};
             rm.M = M;
             if constexpr (kPatch) {
@@ -1017,10 +1039,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const uint32_t pa = (uint32_t)(gk / SA) & 1u;
                 const int s_b = gk % sb, u_b = gk / sb;                 // weight stage and its use index
                 if (lane == 0 && w == 0) TC_TRACE(0, gk, 0);
-                mbar_wait(a_full(sa), pa, 5, gk, prog, 4 + w);
-                if (lane == 0 && w == 0) TC_TRACE(0, gk, 1);
-                mbar_wait(b_full(s_b, u_b), (uint32_t)(u_b >> 1) & 1u, 6, gk, prog, 4 + w);
-                if (lane == 0 && w == 0) TC_TRACE(0, gk, 2);
+                mbar_wait2(a_full(sa), pa, b_full(s_b, u_b), (uint32_t)(u_b >> 1) & 1u, 5, 6, gk, prog, 4 + w);
+                if (lane == 0 && w == 0) { TC_TRACE(0, gk, 1); TC_TRACE(0, gk, 2); }
                 tc_fence_after();
                 const uint32_t a_hi = tmem_base + (uint32_t)(Cfg::A0 + sa * Cfg::ACOLS);
                 const uint32_t a_lo = a_hi + 32u;
@@ -1038,9 +1058,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, 1u);
                         } else if constexpr (Cfg::F16) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);      // 16 fp16 = 32 bytes per k-step, 8 TMEM cells
-                            umma_f16_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
-                            umma_f16_ts(tmem_acc, a_hi + k * 8, db_lo, idesc, 1u);
-                            umma_f16_ts(tmem_acc, a_hi + k * 8, db_hi, idesc, 1u);
+                            const uint32_t d = tmem_acc + (uint32_t)((k % Cfg::CH) * BN);   // this k-step's chain
+                            umma_f16_ts(d, a_lo + k * 8, db_hi, idesc, (i > i_first || k >= Cfg::CH) ? 1u : 0u);
+                            umma_f16_ts(d, a_hi + k * 8, db_lo, idesc, 1u);
+                            umma_f16_ts(d, a_hi + k * 8, db_hi, idesc, 1u);
                         } else if (NPASS == 3) {
                             const uint64_t db_lo = make_smem_desc(b_lo + k * 32);
                             umma_tf32_ts(tmem_acc, a_lo + k * 8, db_hi, idesc, (i > i_first || k > 0) ? 1u : 0u);
@@ -1121,7 +1142,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     if (lane == 0) {                                       // role finished its tile loop (shows as site 0xee on the progress board)
         const int slot = warp < TC_PWARPS ? ((warp & 3) == 0 ? (warp >> 2) : -1) : warp < TC_MMA_WARP ? (warp == TC_PWARPS ? 7 : -1)
                          : warp < TC_AUX_WARP ? 4 + (warp - TC_MMA_WARP) : warp == TC_AUX_WARP ? 6 : 8;
-        if (slot >= 0) prog[slot] = 0xee << 24;
+        if (slot >= 0 && prog != nullptr) prog[slot] = 0xee << 24;
     }
     __syncthreads();
     if (warp == TC_AUX_WARP) {

@@ -1,5 +1,5 @@
 """Perf bring-up for the tcgen05 engine (GPU box; not a pytest file): times single layers with CUDA events.
-   DEFT_TC_DBG=<bits> python tools/tc_perf.py   (bits: 1 no B copy, 2 no A loads, 4 no A stores, 8 no MMA, 16 no epilogue)"""
+   DEFT_TC_DBG=<bits> python tools/tc_perf.py   (bits: 1 no B copy, 2 no A loads, 4 no A stores, 8 no MMA, 16 no epilogue, 32 arm the progress board for stall reports)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tools/ sits next to deft_b200/
 sys.path.insert(0, ROOT)
