@@ -1242,6 +1242,34 @@ static int patch_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, 
     return DEFT_OK;
 }
 
+// ---- 16-channel patch path (TsPatch16AP): 3x3 / stride 1 / pad 1 over one 16-channel source, 3xFP16 image packed from K = 192
+static int patch16_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int M, const Epilogue& ep, unsigned flags, cudaStream_t st) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DEFT_TC_PATCH16"); on = e ? atoi(e) : 1; }
+    if (!on || !patch_enabled() || blob == nullptr || (bn != 16 && bn != 32) || ldw % bn != 0 || ep.Cout % 4 != 0 || ldw > TS_SS_MAXC) return DEFT_EINVAL;
+    if (!tc_blob_is_f16(192, 1, bn) || (flags & DEFT_FLAG_TF32X1)) return DEFT_EINVAL;
+    if (ap.pitch[0] % 4 != 0 || (reinterpret_cast<uintptr_t>(ap.src[0]) & 15) != 0) return DEFT_EINVAL;
+    const long long rows = (long long)ceil_div(ap.W, TP_PW) * ceil_div(ap.H, TP_PH) * TC_BM;
+    if (rows * 100 > (long long)ap.H * ap.W * 115) return DEFT_EINVAL;
+    TmapEncodeFn enc = tmap_encoder();
+    if (enc == nullptr) return DEFT_EINVAL;
+    TsPatch16AP t{};
+    t.H = ap.H; t.W = ap.W;
+    t.tiles_x = ceil_div(ap.W, TP_PW);
+    t.tiles_y = ceil_div(ap.H, TP_PH);
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)ap.W, (cuuint64_t)ap.H, (cuuint64_t)ap.N};
+    const cuuint64_t gstr[3] = {(cuuint64_t)ap.pitch[0] * 4, (cuuint64_t)ap.W * ap.pitch[0] * 4, (cuuint64_t)ap.H * ap.W * ap.pitch[0] * 4};
+    const cuuint32_t box[4] = {16, TP_HW, TP_HH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&t.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ap.src[0]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return DEFT_EINVAL;
+    const int m_tiles = ap.N * t.tiles_x * t.tiles_y;
+    EpiStd epi{ep, nullptr, ldw};
+    return bn == 16 ? ts_launch<TsPatch16AP, 16, 6>(t, blob, 3, M, ldw / bn, 1, epi, st, m_tiles)
+                    : ts_launch<TsPatch16AP, 32, 6>(t, blob, 3, M, ldw / bn, 1, epi, st, m_tiles);
+}
+
 int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K, int M, const Epilogue& ep, unsigned flags, void* scratch,
                      size_t scratch_bytes, cudaStream_t st) {
     for (int i = 0; i < ap.nsrc; ++i)
@@ -1251,6 +1279,10 @@ int tc_conv_dispatch(const ConvAP& ap, const float* blob, int bn, int ldw, int K
         TsC16AP t{};
         t.src = ap.src[0]; t.pitch = ap.pitch[0]; t.N = ap.N; t.H = ap.H; t.W = ap.W; t.OH = ap.OH; t.OW = ap.OW; t.stride = ap.stride;
         if ((long long)ap.N * ap.H * ap.W >= 2147483647LL / 4) return DEFT_EINVAL;
+        if (ap.stride == 1 && ap.OH == ap.H && ap.OW == ap.W) {
+            const int rc16 = patch16_dispatch(ap, blob, bn, ldw, M, ep, flags, st);    // level0: operands from a TMA halo patch
+            if (rc16 != DEFT_EINVAL) return rc16;
+        }
         return ts_dispatch(t, blob, bn, ldw, 192, M, ep, flags, nullptr, 0, st, 1);
     }
     if (ts_enabled() && patch_eligible(ap) && K == 9 * ap.Ctot) {

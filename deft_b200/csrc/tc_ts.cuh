@@ -372,15 +372,39 @@ struct TsDcnPatchAP {
     __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
     __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
 };
+// 3x3 / stride 1 / pad 1 convolution over ONE 16-channel NHWC source (DLA level0 at full resolution) through the halo patch:
+// the same 18 x 10 patch, 64 bytes per pixel (TMA box {16 ch, 18, 10, 1}, SWIZZLE_64B), ONE patch per tile for all nine
+// taps.  K is tap-major as in TsC16AP (k = tap * 16 + c, the weight image packed from K = 192): a 64-wide k-block is four
+// taps, three k-blocks per tile, taps 9..11 are zeros.  Producer thread = output pixel reads 4 x 64 B per k-block with
+// conflict-free LDS.128 instead of TsC16AP's global gathers (16 LDG.128 per lane and k-block, 8 cache lines each, behind a
+// staging transposition): the level0 layer was producer-latency bound at 4.9 k cycles per 128-pixel tile.
+constexpr int TP16_BOX_BYTES = TP_HW * TP_HH * 64;                 // 11520
+constexpr int TP16_STAGE_BYTES = (TP16_BOX_BYTES + 1023) / 1024 * 1024;
+struct TsPatch16AP {
+    static constexpr bool kPatch = true;
+    static constexpr bool kDcn = false;
+    static constexpr bool kC16 = true;
+    static constexpr int kHW = TP_HW, kHH = TP_HH, kHalo = 1, kBoxBytes = TP16_BOX_BYTES, kStageBytes = TP16_STAGE_BYTES;
+    static constexpr int kExtraSmemBytes = 0;
+    alignas(64) CUtensorMap tmap;                                  // dims {16, W, H, N} of the NHWC source
+    int H, W, tiles_x, tiles_y;
+    __device__ __forceinline__ int ktaps() const { return 1; }
+    __device__ __forceinline__ void setup_once(unsigned char*) {}
+    __device__ __forceinline__ void tile_init(int, int, unsigned char*, int, int, int4*) {}
+    __device__ __forceinline__ void fill(int, int, int, const int4*, float*) const {}
+};
 template <class AP, bool P = AP::kPatch>
 struct TsPG {                                                      // patch geometry of an A producer (none for the gather producers)
-    static constexpr bool DCN = false;
-    static constexpr int HW = 1, HALO = 0, BOX = 0, STAGE = 0;
+    static constexpr bool DCN = false, C16 = false;
+    static constexpr int HW = 1, HALO = 0, BOX = 0, STAGE = 0, KPP = 1;
 };
+template <class AP, class = void> struct TsIsC16 { static constexpr bool value = false; };
+template <class AP> struct TsIsC16<AP, typename std::enable_if<AP::kC16>::type> { static constexpr bool value = true; };
 template <class AP>
 struct TsPG<AP, true> {
-    static constexpr bool DCN = AP::kDcn;
+    static constexpr bool DCN = AP::kDcn, C16 = TsIsC16<AP>::value;
     static constexpr int HW = AP::kHW, HALO = AP::kHalo, BOX = AP::kBoxBytes, STAGE = AP::kStageBytes;
+    static constexpr int KPP = C16 ? 3 : 9;                         // k-blocks that share one patch (one tile's taps / one channel block's taps)
 };
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
@@ -565,8 +589,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
     constexpr int SA = Cfg::SA;
     constexpr bool kPatch = AP::kPatch;
     using PG = TsPG<AP>;
-    constexpr int P_SUB = PG::STAGE;                               // one 32-channel halo patch
-    constexpr int P_STAGE = Cfg::F16 ? 2 * P_SUB : P_SUB;          // halo patch of one k-block's channels
+    constexpr int P_SUB = PG::STAGE;                               // one 32-channel (C16: 16-channel) halo patch
+    constexpr int P_STAGE = (Cfg::F16 && !PG::C16) ? 2 * P_SUB : P_SUB;   // halo patch of one k-block's channels
+    constexpr int KPP = PG::KPP;
     // the gather producers keep per-thread state in their AP (private copy); the patch AP holds the TMA descriptor,
     // which must stay in param space
     typename std::conditional<kPatch, const AP&, AP>::type ap = ap_param;
@@ -781,6 +806,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
             const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
             const int r = quad * 32 + lane, ry = r >> 4, rx = r & 15;
             int gk0 = 0, gc0 = 0;
+            // p_empty expects all 16 producer warps per patch.  With three k-blocks per patch (C16) one of the four k-groups has no
+            // k-block in it: its warps release the patch too -- after waiting for p_full, so that the arrival cannot land in the
+            // phase of the stage's previous use (the loader issues use u+1 only once use u has been released by everyone).
+            auto skip_patch = [&](int gc) {
+                mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_empty(gc % ps));
+            };
             for (int t = blockIdx.x; t < ts.total; t += gridDim.x) {
                 const int z = t / tiles_mn;
                 const int kb0 = z * ts.kb_per_split;
@@ -789,13 +822,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const float* pbase = nullptr;
                 int i = (grp - (gk0 % TS_KGROUPS) + TS_KGROUPS) % TS_KGROUPS;
                 for (; i < nkb; i += TS_KGROUPS) {
-                    const int c = i / 9, tap = i - c * 9;
+                    const int c = i / KPP, tap = i - c * KPP;                 // C16: tap = k-block of the tile (taps 4 tap .. 4 tap + 3)
                     if (tid == grp * 128) TC_TRACE(1, gk0 + i, 0);
                     if (c != last_c) {
                         if (last_c >= 0) {                 // done with the previous channel block's patch
                             __syncwarp();
                             if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
                         }
+                        for (int pc = last_c + 1; pc < c; ++pc) skip_patch(gc0 + pc);     // patches without a k-block of this group (KPP < 4)
                         const int gc = gc0 + c;
                         mbar_wait(p_full(gc % ps), (uint32_t)(gc / ps) & 1u, 1, gc, quad == 0 ? prog : nullptr, grp);
                         pbase = reinterpret_cast<const float*>(smem + (size_t)(gc % ps) * P_STAGE);
@@ -810,7 +844,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     const float* prow = pbase + idx * 32;
                     const int sw = idx & 7;
                     float4 x[8];
-                    if (!(dbg & 2)) {
+                    // C16: half h of the k-block = taps 4 tap + 2 h, + 1: 2 x 64 B of the 16-channel patch (SWIZZLE_64B: 16-byte chunk ^ ((pixel >> 1) & 3))
+                    auto load16 = [&](int h) {
+#pragma unroll
+                        for (int tq = 0; tq < 2; ++tq) {
+                            const int t16 = 4 * tap + 2 * h + tq;
+                            if (t16 < 9) {
+                                const int ky16 = t16 / 3, kx16 = t16 - ky16 * 3;
+                                const int i16 = (ry + ky16) * TP_HW + rx + kx16;
+                                const float* p16 = pbase + i16 * 16;
+                                const int s16 = (i16 >> 1) & 3;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) x[tq * 4 + q] = *reinterpret_cast<const float4*>(p16 + ((q ^ s16) << 2));
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) x[tq * 4 + q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                    };
+                    if constexpr (PG::C16) {
+                        load16(0);
+                    } else if (!(dbg & 2)) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow + ((q ^ sw) << 2));
                     } else {
@@ -827,9 +881,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             if (h == 1) {
-                                const float* prow1 = prow + P_SUB / 4;
+                                if constexpr (PG::C16) {
+                                    load16(1);
+                                } else {
+                                    const float* prow1 = prow + P_SUB / 4;
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow1 + ((q ^ sw) << 2));
+                                    for (int q = 0; q < 8; ++q) x[q] = *reinterpret_cast<const float4*>(prow1 + ((q ^ sw) << 2));
+                                }
                             }
 #pragma unroll
                             for (int q = 0; q < 2; ++q) {
@@ -867,8 +925,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(p_empty((gc0 + last_c) % ps));
                 }
+                for (int pc = last_c + 1; pc < nkb / KPP; ++pc) skip_patch(gc0 + pc);
                 gk0 += nkb;
-                gc0 += nkb / 9;
+                gc0 += nkb / KPP;
             }
         } else {
         const int quad = warp & 3, grp = warp >> 2;
@@ -1120,12 +1179,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
                 const int y0 = (tr / ap.tiles_x) * TP_PH - PG::HALO, x0 = (tr % ap.tiles_x) * TP_PW - PG::HALO;
                 const int kb0 = z * ts.kb_per_split;
                 const int nkb = min(ts.nkb_total, kb0 + ts.kb_per_split) - kb0;
-                const int c0 = kb0 / 9, nch = nkb / 9;
+                const int c0 = kb0 / KPP, nch = nkb / KPP;
                 for (int c = 0; c < nch; ++c, ++gc) {
                     const int s = gc % ps;
                     mbar_wait(p_empty(s), ((uint32_t)(gc / ps) & 1u) ^ 1u, 8, gc, prog, 8);
                     if (elect_one_sync()) {
-                        if constexpr (Cfg::F16) {          // 64 channels per k-block: two 32-channel boxes into the two halves of the stage
+                        if constexpr (PG::C16) {           // the tile's one 16-channel patch
+                            mbar_arrive_expect_tx(p_full(s), (uint32_t)PG::BOX);
+                            tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE, &ap_param.tmap, 0, x0, y0, n, p_full(s));
+                        } else if constexpr (Cfg::F16) {   // 64 channels per k-block: two 32-channel boxes into the two halves of the stage
                             mbar_arrive_expect_tx(p_full(s), (uint32_t)(2 * PG::BOX));
                             tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE, &ap_param.tmap, (c0 + c) * 64, x0, y0, n, p_full(s));
                             tma_load_4d(raw_addr + pad + (uint32_t)s * P_STAGE + P_SUB, &ap_param.tmap, (c0 + c) * 64 + 32, x0, y0, n, p_full(s));
@@ -1154,12 +1216,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_ts_kernel(const __grid_const
 template <class AP, int BN, int NPASS>
 static int ts_launch(const AP& ap, const float* blob, int nkb, int M, int n_tiles, int splits, EpiStd epi, cudaStream_t st, int m_tiles_override = 0) {
     using Cfg = TsCfg<BN, NPASS>;
-    constexpr int ps = AP::kPatch ? (Cfg::F16 ? 2 : TP_MAX_STAGES) : 0;
-    constexpr int P_STAGE = (Cfg::F16 ? 2 : 1) * TsPG<AP>::STAGE;
+    constexpr int ps = AP::kPatch ? ((Cfg::F16 && !TsPG<AP>::C16) ? 2 : TP_MAX_STAGES) : 0;
+    constexpr int P_STAGE = ((Cfg::F16 && !TsPG<AP>::C16) ? 2 : 1) * TsPG<AP>::STAGE;
     const int fixed = 1024 /*align*/ + 512 /*barriers*/ + TS_EPI_SMEM + (AP::kPatch ? ps * P_STAGE : TS_COMMON_SMEM) + AP::kExtraSmemBytes;
     TileSched ts{};
     ts.kb_per_split = ceil_div(nkb, splits);
-    if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, 9) * 9;      // whole channel blocks per split
+    if (AP::kPatch) ts.kb_per_split = ceil_div(ts.kb_per_split, TsPG<AP>::KPP) * TsPG<AP>::KPP;      // whole channel blocks (patches) per split
     ts.splits = ceil_div(nkb, ts.kb_per_split);
     ts.m_tiles = m_tiles_override > 0 ? m_tiles_override : ceil_div(M, TC_BM);
     ts.n_tiles = n_tiles;

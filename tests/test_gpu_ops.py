@@ -54,7 +54,10 @@ def test_layout_roundtrip(dev):
                                                   (256, 256, 3, 1, (6, 8)), (512, 512, 3, 1, (3, 4)),
                                                   # 16x8-patch (TMA halo) producer: exact / ragged tilings, split-K, narrow N
                                                   (64, 64, 3, 1, (30, 62)), (128, 64, 3, 1, (16, 32)), (256, 128, 3, 1, (30, 62)),
-                                                  (64, 32, 3, 1, (32, 48))])
+                                                  (64, 32, 3, 1, (32, 48)),
+                                                  # 16-channel halo patch (TsPatch16AP: DLA level0): exact / ragged tilings, N = 16 and 32
+                                                  (16, 16, 3, 1, (32, 48)), (16, 16, 3, 1, (30, 62)), (16, 32, 3, 1, (24, 64)),
+                                                  (16, 16, 3, 1, (160, 256))])      # 640 patches: 4-5 tiles per CTA (the patch ring wraps)
 def test_conv_bn_act(dev, cin, cout, k, stride, hw, flags):
     from deft_b200 import ops, packing
     sp = {}
