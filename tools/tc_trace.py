@@ -8,7 +8,7 @@ from deft_b200 import ops, packing
 from oracle import spec
 
 CASES = {"conv32": ("conv", 64, 32, 3, 152, 272), "conv64": ("conv", 64, 64, 3, 152, 272), "conv128": ("conv", 128, 128, 3, 76, 136), "conv1x1": ("conv", 128, 64, 1, 152, 272),
-         "dcn64": ("dcn", 64, 64, 3, 152, 272), "dcn128": ("dcn", 128, 128, 3, 76, 136)}
+         "conv16": ("conv", 16, 16, 3, 608, 1088), "dcn64": ("dcn", 64, 64, 3, 152, 272), "dcn128": ("dcn", 128, 128, 3, 76, 136)}
 case = sys.argv[1] if len(sys.argv) > 1 else "conv64"
 kind, cin, cout, k, H, W = CASES[case]
 dev = torch.device("cuda:0")
@@ -20,7 +20,7 @@ if kind == "conv":
     wp, ldw = packing.pack_conv(w.to(dev))
     sc, sh = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
     M = H * W
-    w_tc, bn = ops.tc_pack(wp, ldw, wp.shape[0], M, taps=k * k)
+    w_tc, bn = ops.conv_tc_pack(wp, ldw, cin, k, k, M)
     fn = lambda: ops.conv2d_bn_act([x], wp, ldw, sc, sh, cout, k, k, 1, k // 2, True, out=out, flags=2, w_tc=w_tc, tc_bn=bn)
 else:
     sp = {}
