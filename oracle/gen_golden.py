@@ -8,7 +8,9 @@ generic_decode (imported from /root/reference/src/lib through oracle/ref_loader.
 torchvision.ops.deform_conv2d shim) and torch.nn.LSTM/Linear assembled as
 utils/tracking_utils/kalman_filter_lstm.py:9-29 does (that file itself is un-importable: it
 imports the broken model.model).  Weights/inputs are the seeded synthetic tensors of oracle/spec.py, so
-the GPU box regenerates identical bits without the reference.
+the GPU box regenerates identical bits without the reference.  The tracker-side logic (rows f1 / f3: FeatureRecorder,
+STrack.get_similarity, matching.fuse_motion) lives in un-importable modules too; gen_tracker_logic() cuts those definitions out
+of the reference source with `ast` and executes them unmodified (tests/golden/tracker_logic.pt).
 """
 import json
 import os
@@ -181,6 +183,117 @@ def gen_afe_train():
     print("afe train forward/loss ok:", g["loss"])
 
 
+# --------------------------------------------------------------------------- f1 / f3: the tracker's own code, extracted
+# utils/tracker.py and utils/matching.py cannot be imported here (they need `lap`, `cython_bbox`, `progress`, `nuscenes`, and
+# tracker.py parses argv at import).  The pieces the product restates are plain numpy though, so they are cut out of the
+# reference SOURCE with `ast` (class / function definitions and the module constants they read, nothing rewritten) and
+# executed as they stand: FeatureRecorder + Node (tracker.py:29-137), STrack.get_similarity (219-252), matching.fuse_motion
+# (matching.py:311-364), KalmanFilterLSTM.gating_distance (kalman_filter_lstm.py:80-103), chi2inv95 (kalman_filter.py:9-19).
+REF_LIB = "/root/reference/src/lib"
+
+
+def _extract(path, top_names=(), class_methods=()):
+    """Source of the named top-level assignments / classes / functions of `path`, plus `Class.method` definitions re-rooted as
+    top-level functions -- compiled from the unmodified AST nodes."""
+    import ast
+    tree = ast.parse(open(path).read())
+    picked = []
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and any(isinstance(t, ast.Name) and t.id in top_names for t in node.targets):
+            picked.append(node)
+        elif isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in top_names:
+            picked.append(node)
+        elif isinstance(node, ast.ClassDef):
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and (node.name, sub.name) in class_methods:
+                    picked.append(sub)
+    mod = ast.Module(body=picked, type_ignores=[])
+    return compile(ast.fix_missing_locations(mod), path, "exec")
+
+
+def load_tracker_logic():
+    """Namespace with the reference's own FeatureRecorder, Node, get_similarity, fuse_motion, gating_distance."""
+    import types
+    import scipy.linalg
+    ns = {"np": np, "scipy": __import__("scipy")}
+    exec(_extract(os.path.join(REF_LIB, "utils", "tracker.py"), ("Max_record_frame", "decay", "decay2", "max_track_node", "Node", "FeatureRecorder"),
+                  (("STrack", "get_similarity"),)), ns)
+    kf_ns = {}
+    exec(_extract(os.path.join(REF_LIB, "utils", "tracking_utils", "kalman_filter.py"), ("chi2inv95",)), kf_ns)
+    ns["kalman_filter"] = types.SimpleNamespace(chi2inv95=kf_ns["chi2inv95"])
+    exec(_extract(os.path.join(REF_LIB, "utils", "matching.py"), ("fuse_motion",)), ns)
+    exec(_extract(os.path.join(REF_LIB, "utils", "tracking_utils", "kalman_filter_lstm.py"), (), (("KalmanFilterLSTM", "gating_distance"),)), ns)
+    return ns
+
+
+def tracker_sequence(dataset, seed):
+    """A synthetic video for the recorder: frame indices with gaps (so both decay branches and the 50-frame eviction run),
+    2..7 detections per frame, and a stub model whose forward_stacker_features returns seeded float32 affinities."""
+    rng = np.random.RandomState(seed)
+    frames, f = [], 0
+    for k in range(58):
+        frames.append(f)
+        f += 1 if rng.rand() < 0.8 else int(rng.randint(2, 5))
+    counts = {fr: int(rng.randint(2, 6)) for fr in frames}
+    return frames, counts
+
+
+def gen_tracker_logic():
+    import types
+    ns = load_tracker_logic()
+    out = {"constants": {k: ns[k] for k in ("Max_record_frame", "decay", "decay2", "max_track_node")}, "recorder": {}, "fuse_motion": []}
+    for dataset, seed in (("mot", 11), ("kitti_tracking", 12), ("nuscenes", 13)):
+        frames, counts = tracker_sequence(dataset, seed)
+        rng = np.random.RandomState(seed + 100)
+        aff = {}                                     # (frame, pre_frame) -> what the stub model returned
+
+        class StubAFE:
+            def forward_stacker_features(self, prev, cur, fill_up_column=False):
+                assert fill_up_column is False
+                a = rng.rand(len(prev), len(cur) + 1).astype(np.float32)
+                aff[(int(cur[0, 0]), int(prev[0, 0]))] = a
+                return a
+        model = types.SimpleNamespace(AFE=StubAFE())
+        rec = ns["FeatureRecorder"](dataset)
+        checks = []
+        trng = np.random.RandomState(seed + 200)
+        for fi in frames:
+            feats = np.full((counts[fi], 4), fi, dtype=np.float32)          # row 0 col 0 carries the frame index for the stub
+            rec.update(model, fi, feats, np.zeros((counts[fi], 4), dtype=np.float32))
+            pos = frames.index(fi)
+            if not (pos in (3, 9) or pos % 8 == 7 or pos >= len(frames) - 2):    # a dozen check frames incl. before / after the eviction starts
+                continue
+            sim = {int(k): v.copy() for k, v in rec.all_similarity[fi].items()}
+            # tracks: node lists (oldest first) over frames still on record, incl. single-node and > 5-node tracks and nodes
+            # older than max_track_node frames are impossible here (record <= 50 frames) -- the skip branch is covered by
+            # the restatement's own property test
+            tracks = []
+            on_record = [int(x) for x in rec.all_frame_index[:-1]]
+            for _ in range(6):
+                k = int(trng.randint(1, min(9, len(on_record)) + 1))
+                fs = sorted(trng.choice(on_record, size=k, replace=False).tolist())
+                nodes = [(f_, int(trng.randint(0, counts[f_]))) for f_ in fs]
+                stub = types.SimpleNamespace(nodes=[ns["Node"](f_, i_) for f_, i_ in nodes], dataset=dataset)
+                res = ns["get_similarity"](stub, fi, rec)
+                tracks.append({"nodes": nodes, "similarity": None if res is None else np.asarray(res).copy()})
+            checks.append({"frame": fi, "aff": {int(pre): aff[(fi, int(pre))].copy() for pre in sim}, "all_similarity": sim, "tracks": tracks})
+        out["recorder"][dataset] = {"frames": frames, "counts": counts, "checks": checks}
+    # fuse_motion (use_lstm=True as tracker.py:906-913 calls it; lambda_ default), both observation-count branches
+    rng = np.random.RandomState(77)
+    for T, m in ((6, 5), (1, 3), (9, 12)):
+        cost = rng.rand(T, m).astype(np.float64)
+        pred = rng.rand(T, 4) * np.array([40.0, 30.0, 1.0, 1.0])
+        n_obs = [int(x) for x in rng.choice([1, 5, 299, 300, 301, 1000], size=T)]
+        det = rng.rand(m, 4) * np.array([40.0, 30.0, 1.0, 50.0])
+        tracks = [types.SimpleNamespace(observations=[0] * n_obs[i], covariance=np.eye(4, 4), prediction_at_frame=(lambda fr, i=i: pred[i].copy())) for i in range(T)]
+        dets = [types.SimpleNamespace(to_xyah=(lambda j=j: det[j].copy())) for j in range(m)]
+        kf = types.SimpleNamespace(gating_distance=lambda *a, **k: ns["gating_distance"](None, *a, **k))
+        res = ns["fuse_motion"](kf, cost.copy(), tracks, dets, frame_id=7, use_lstm=True)
+        out["fuse_motion"].append({"cost": cost, "pred": pred, "n_obs": n_obs, "det": det, "fused": np.asarray(res).copy()})
+    torch.save(out, os.path.join(OUT, "tracker_logic.pt"))
+    print("tracker logic ok:", {k: len(v["checks"]) for k, v in out["recorder"].items()}, len(out["fuse_motion"]), "fuse_motion cases")
+
+
 def main():
     if not ref_loader.available():
         sys.exit("reference not present; goldens can only be generated in the build container")
@@ -193,6 +306,7 @@ def main():
     gen_decode_plateau()
     gen_lstm()
     gen_afe_train()
+    gen_tracker_logic()
 
 
 if __name__ == "__main__":

@@ -376,9 +376,12 @@ def afe_loss(inp, target, mask0, mask1, max_object):
 
 
 # --------------------------------------------------------------------------- f1: recorder decay + per-track median
-# PARITY UNPINNED BY A RUNNING REFERENCE: utils/tracker.py cannot be imported here (it needs `lap`, `cython_bbox`, `progress`
-# and parses sys.argv at import: SURVEY.md section 8(c)), and the reference holds no test vectors for it.  The two functions
-# below restate the cited lines; tests/test_oracle_cpu.py checks their row-selection / decay rules against hand-built cases.
+# utils/tracker.py cannot be imported here (it needs `lap`, `cython_bbox`, `progress` and parses sys.argv at import: SURVEY.md
+# section 8(c)) and the reference holds no test vectors for it.  PINNED nevertheless: oracle/gen_golden.py::gen_tracker_logic cuts
+# FeatureRecorder, Node and STrack.get_similarity out of the reference source with `ast`, runs them unmodified on a synthetic
+# 58-frame video per dataset and stores inputs + outputs in tests/golden/tracker_logic.pt; tests/test_oracle_cpu.py holds the
+# two functions below to it (row selection + medians bit-exact; the decayed similarities to one float32 rounding, because
+# numpy 2 promotes the reference's float32-array x np.float64-scalar product to float64 where its numpy 1.x kept float32).
 def recorder_similarity(aff_by_frame, frame_index, dataset="mot", decay=1.0, decay2=0.01):
     """FeatureRecorder.update's loop (utils/tracker.py:76-90; constants 22-25): aff_by_frame {pre_index: np[n_pre, m+1]}
     (forward_stacker_features(..., fill_up_column=False)) -> {pre_index: similarity * delta}, float32 like the reference
@@ -445,9 +448,11 @@ def warp_affine_bilinear(img_u8_hwc, inv_affine, H, W):
 
 
 # --------------------------------------------------------------------------- f3: motion fusion + linear assignment
-# PARITY UNPINNED BY A RUNNING REFERENCE: utils/matching.py needs `lap` (requirements.txt:14, unpinned, absent) and
-# `cython_bbox`.  fuse_motion is restated line by line; lapjv(extend_cost, cost_limit) is restated as the exact solution of
-# lap's extended problem and checked against brute force (tests/test_oracle_cpu.py).
+# utils/matching.py needs `lap` (requirements.txt:14, unpinned, absent) and `cython_bbox`: it does not import.
+# fuse_motion_lstm is PINNED like the f1 functions (the reference's own matching.fuse_motion + KalmanFilterLSTM.gating_distance,
+# cut out with `ast` and run by gen_tracker_logic: bit-exact in float64, both observation-count branches, inf gating included).
+# linear_assignment stays PARITY UNPINNED BY A RUNNING REFERENCE: lap.lapjv itself is absent; lapjv(extend_cost, cost_limit) is
+# restated as the exact solution of lap's extended problem and checked against brute force (tests/test_oracle_cpu.py).
 CHI2INV95_2 = 5.9915                                         # kalman_filter.py:13-15 (chi2inv95[2])
 
 

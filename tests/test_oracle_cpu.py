@@ -172,6 +172,53 @@ def test_track_similarity_restatement_properties():
     assert np.array_equal(restate.track_similarity(nodes[-4:], 10, rec, dataset="nuscenes"), np.median(rows[-2:], axis=0))
 
 
+def test_tracker_restatements_vs_the_reference_tracker_code_golden():
+    """Rows f1 / f3 pinned: tests/golden/tracker_logic.pt holds outputs of the reference's OWN FeatureRecorder.update,
+    STrack.get_similarity (utils/tracker.py:46-90, 219-252) and matching.fuse_motion + KalmanFilterLSTM.gating_distance
+    (matching.py:311-364, kalman_filter_lstm.py:80-103) -- the definitions are cut out of the reference source with `ast` and run
+    unmodified by oracle/gen_golden.py::gen_tracker_logic (the modules themselves do not import).
+    One environment effect: `pre_similarity * delta` is float32-array x numpy-float64-scalar (delta inherits np.int64 frame
+    indices).  The reference's numpy 1.x (environment.yml) keeps that product float32 (value-based casting); the numpy 2 of this
+    container promotes it to float64 (NEP 50), so the golden holds f64(sim) * delta.  The restatement (and the device kernel)
+    follow the reference's environment: float32.  Hence: decayed similarities within one float32 rounding of the golden and
+    bit-equal where delta = 1; the per-track row selection + medians bit-exact on the golden's own similarities; fuse_motion
+    (float64 on both sides) bit-exact."""
+    g = torch.load(os.path.join(GOLDEN, "tracker_logic.pt"), weights_only=False)
+    assert g["constants"] == {"Max_record_frame": 50, "decay": 1.0, "decay2": 0.01, "max_track_node": 50}
+    n_tracks = 0
+    for dataset, rec in g["recorder"].items():
+        frames = rec["frames"]
+        for chk in rec["checks"]:
+            fi = chk["frame"]
+            on_record = frames[max(0, frames.index(fi) - 49): frames.index(fi)]              # <= 50 frames on record incl. the current one
+            assert sorted(chk["all_similarity"]) == on_record
+            sim = restate.recorder_similarity(chk["aff"], fi, dataset=dataset)
+            assert sorted(sim) == on_record
+            m_frame = {"mot": 10, "kitti_tracking": 5, "nuscenes": 3}[dataset]
+            for pre in on_record:
+                ref = chk["all_similarity"][pre]
+                assert sim[pre].dtype == np.float32
+                if fi - pre < m_frame:                                                       # decay = 1.0: the product is the affinity itself
+                    assert np.array_equal(sim[pre], ref), (dataset, fi, pre)
+                else:
+                    assert np.array_equal(sim[pre], (chk["aff"][pre] * np.float32(pow(0.01, (fi - pre) / 3.0))).astype(np.float32))
+                    assert np.all(np.abs(sim[pre].astype(np.float64) - ref) <= 1.3e-7 * np.abs(ref) + 2e-38), (dataset, fi, pre)   # delta and the product each round once to float32; below 1.2e-38 float32 is denormal
+            for tr in chk["tracks"]:
+                got = restate.track_similarity(tr["nodes"], fi, chk["all_similarity"], dataset=dataset)
+                assert (got is None) == (tr["similarity"] is None)
+                if got is not None:
+                    assert np.array_equal(got, tr["similarity"]), (dataset, fi, tr["nodes"])
+                    f32 = restate.track_similarity(tr["nodes"], fi, sim, dataset=dataset)     # the float32 chain the device kernel mirrors
+                    assert np.allclose(f32, tr["similarity"], rtol=1e-6, atol=1e-30)
+                    n_tracks += 1
+    assert n_tracks > 150
+    for case in g["fuse_motion"]:
+        got = restate.fuse_motion_lstm(case["cost"], case["pred"][:, :2], case["n_obs"], case["det"][:, :2])
+        assert np.array_equal(np.isinf(got), np.isinf(case["fused"]))
+        assert np.array_equal(got[np.isfinite(got)], case["fused"][np.isfinite(case["fused"])])
+        assert np.isinf(case["fused"]).any() or case["cost"].shape[0] == 1
+
+
 def test_preprocess_restatement_vs_cv2():
     """Row f2 oracle: the restated bilinear warp stays within cv2.warpAffine's 1/32-pixel fixed-point error (the
     reference calls cv2: detector.py:399-407); the normalisation is detector.py:408-410 verbatim."""
