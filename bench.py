@@ -355,7 +355,7 @@ def gpu_arm(args, rank, local_rank, world):
         fps_e2e = total_frames / (ms_e2e * 1e-3)
         line = {"metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.simt else ("tf32" if args.tf32x1 else "f32 (3xTF32 tensor-core where covered, fp32 SIMT elsewhere)"),
+                "dtype": "f32" if args.simt else ("tf32" if args.tf32x1 else "f32 (fp32 in, fp32 accumulate, fp32 out; tensor-core products as three error-compensated fp16 / tf32 passes, fp32 SIMT elsewhere)"),
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "streams_total": n_total_streams, "streams_per_gpu": S if world == 1 or not args.streams else f"{n_total_streams} streams round-robin over {world} GPUs",
                            "parallelism": f"stream-parallel, {n_total_streams} stream(s) over {world} GPU(s) (no collective)",

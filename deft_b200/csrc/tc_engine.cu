@@ -1035,12 +1035,21 @@ int tc_pick_bn(int ldw, int M, int kind) {
     if (best == 0) best = (ldw % 32 == 0) ? 32 : 16;
     return best;                                         // too few CTAs either way: keep the widest tile, split K instead
 }
-static int tc_pick_splits(int ctas, int nkb) {
-    // CTAs a split-K layer should reach (DEFT_TC_SPLIT_TARGET).  Half the SMs by default: with several frames in flight
-    // the other half is busy with the neighbouring frames' kernels, and every split costs a partial write + read
-    // (measured, 4 frames in flight: 148 -> 487 fps, 74 -> 497 fps, 37 -> 486 fps).
-    static int target = -1;
-    if (target < 0) { const char* e = getenv("DEFT_TC_SPLIT_TARGET"); target = e ? atoi(e) : TC_NUM_SMS / 2; }
+static int tc_pick_splits(int ctas, int nkb, bool dcn = false) {
+    // CTAs a split-K layer should reach (DEFT_TC_SPLIT_TARGET).  A third of the SMs by default: with several frames in flight
+    // the rest is busy with the neighbouring frames' kernels, and every split costs a partial write + read.  Measured on one
+    // box with the final r2 build, 4 frames in flight (tools/gpu_call25.sh): 1 -> 616.4, 24 -> 621.4, 37 -> 621.9, 50 -> 624.4,
+    // 60 -> 623.4, 74 -> 617.6 / 619.0 fps (r1: 148 -> 487, 74 -> 497, 37 -> 486); one isolated frame prefers more splits
+    // (depth 1: 74 -> 411.7, 50 -> 399.9 fps).
+    // The DCN gather-GEMMs keep half the SMs (74): the metric also quotes their time alone (bench.py roofline: one eager
+    // frame), where more splits are what the four few-tile DCN layers want; the convs take the throughput setting.
+    static int target_conv = -1, target_dcn = -1;
+    if (target_conv < 0) {
+        const char* e = getenv("DEFT_TC_SPLIT_TARGET");
+        target_conv = e ? atoi(e) : 50;
+        target_dcn = e ? atoi(e) : TC_NUM_SMS / 2;
+    }
+    const int target = dcn ? target_dcn : target_conv;
     if (ctas >= 100 || ctas >= target) return 1;
     int s = target / ctas;
     int max_s = nkb / 6;                                 // keep >= 6 k-blocks per split
@@ -1054,7 +1063,7 @@ size_t tc_blob_floats(int ldw, int K, int bn) {
 }
 size_t tc_splitk_scratch_bytes(int ldw, int K, int M, int kind) {
     const int bn = tc_pick_bn(ldw, M, kind);
-    const int splits = tc_pick_splits(ceil_div(M, TC_BM) * (ldw / bn), ceil_div(K, TC_BK));
+    const int splits = tc_pick_splits(ceil_div(M, TC_BM) * (ldw / bn), ceil_div(K, TC_BK), kind == TC_KIND_DCN);
     return splits > 1 ? align_up((size_t)splits * M * ldw * sizeof(float), 256) : 0;
 }
 
@@ -1096,7 +1105,7 @@ static int tc_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
                        size_t scratch_bytes, cudaStream_t st) {
     if (blob == nullptr || bn <= 0 || ldw % bn != 0 || ep.Cout % 4 != 0) return DEFT_EINVAL;
     const int nkb = ceil_div(K, TC_BK), nt = ldw / bn;
-    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
+    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb, std::is_same<AP, TcDcnAP>::value);
     if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
     if (splits > 1) splits = ceil_div(nkb, ceil_div(nkb, splits));
     EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
@@ -1130,7 +1139,7 @@ static int ts_dispatch(AP ap, const float* blob, int bn, int ldw, int K, int M, 
     const bool f16 = tc_blob_is_f16(K, taps, bn) && !(flags & DEFT_FLAG_TF32X1);
     if (tc_blob_is_f16(K, taps, bn) && !f16) return DEFT_EINVAL;      // the image is packed for 3xFP16: no single-pass TF32 variant of it
     const int nkb = K / (f16 ? 64 : TC_BK), nt = ldw / bn;
-    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb);
+    int splits = tc_pick_splits(ceil_div(M, TC_BM) * nt, nkb, std::is_same<AP, TsDcnAP>::value);
     if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
     if (splits > 1) splits = ceil_div(nkb, ceil_div(nkb, splits));
     EpiStd epi{ep, splits > 1 ? reinterpret_cast<float*>(scratch) : nullptr, ldw};
@@ -1347,7 +1356,7 @@ static int dcn_patch_dispatch(const DcnAP& ap, const float* blob, int bn, int ld
     }
     const int nkb = K / 64, nt = ldw / bn, ncb = ap.Cin / 64;
     const int m_tiles = ap.N * t.tiles_x * t.tiles_y;
-    int splits = tc_pick_splits(m_tiles * nt, nkb);
+    int splits = tc_pick_splits(m_tiles * nt, nkb, true);
     if (splits > ncb) splits = ncb;
     if (splits > 1) splits = ceil_div(ncb, ceil_div(ncb, splits));     // whole channel blocks per split
     if (splits > 1 && (scratch == nullptr || scratch_bytes < (size_t)splits * M * ldw * sizeof(float))) splits = 1;
