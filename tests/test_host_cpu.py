@@ -41,6 +41,14 @@ def test_host_only_entry_points_without_a_gpu(monkeypatch):
     assert l.deft_tc_tile_n(1280, M, 2) == 256                                                         # fused heads: one head per N tile
     assert l.deft_dcnv2_workspace_bytes(1, 152, 272, 64, 64) >= M * 32 * 4                               # at least the offset/mask map
     assert l.deft_tc_scratch_bytes(512, 9 * 512, 19 * 34, 0) >= 2 * 19 * 34 * 512 * 4                    # deep layer: split-K partials
+    # split-K policy (tc_pick_splits): a DCN gather-GEMM of the same shape is never given FEWER partial buffers than a conv
+    # (DCN layers split up to half the SMs, convs up to a third) and a map with >= 100 tiles gets none at all
+    assert l.deft_tc_scratch_bytes(128, 9 * 256, 38 * 68, 1) >= l.deft_tc_scratch_bytes(128, 9 * 256, 38 * 68, 0) > 0
+    assert l.deft_tc_scratch_bytes(64, 9 * 64, M, 0) == 0 and l.deft_tc_scratch_bytes(64, 9 * 64, M, 1) == 0
+    # the second DCN gather kernel is opt-in and its launch counter starts at zero in a process that never launched it
+    assert l.deft_dcn_patch_launch_count() == 0
+    l.deft_debug_set_dcn_patch(2)
+    l.deft_debug_set_dcn_patch(0)
 
 
 @pytest.mark.parametrize("heads,dataset", [(spec.MOT_HEADS, "mot"), (spec.KITTI_HEADS, "kitti"), (spec.NUSC_HEADS, "nuscenes")])
