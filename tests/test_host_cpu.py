@@ -197,3 +197,20 @@ def test_bench_stream_assignment_for_the_nuscenes_split():
     import bench
     nf, ni, nc = bench.synthetic_tracks(500, 5, 100, 6, 5)
     assert int(nc.min()) == 1 and int(nc.max()) == 5 and int(nf[nf >= 0].min()) == 0 and int(nf.max()) == 4
+
+
+def test_bench_cpu_arm_picks_a_usable_thread_count():
+    """bench.py's CPU arm (cpu_baseline / --impl reference) must run the reference at its best on the box: never more threads
+    than the affinity mask / cgroup quota allow, and the probe keeps the fastest of the candidate counts (a 128-CPU container
+    with 128 threads was 12x slower per frame than 8 threads here)."""
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= (os.cpu_count() or 1) and n <= len(os.sched_getaffinity(0))
+    before = torch.get_num_threads()
+    try:
+        best, table = bench.pick_cpu_threads(torch)
+        assert best in table and max(table) == n and torch.get_num_threads() == best
+        assert all(v > 0 for v in table.values())
+        assert table[best] <= min(table.values()) / 0.97 + 1e-9          # within the 3 % preference for more threads
+    finally:
+        torch.set_num_threads(before)
