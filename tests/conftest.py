@@ -25,6 +25,31 @@ def nerr(a, b):
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def oracle_threads():
+    """Thread count for the CPU oracle inside GPU tests: what this process can really run on (affinity mask, cgroup quota),
+    at most 32.  A pool box shows 128 CPUs to a container that may own a fraction of them; 128 OpenMP threads there made a
+    full-size oracle frame 12x slower than 8 threads (bench.py::usable_cores has the same logic)."""
+    n = os.cpu_count() or 8
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for quota_path, period_path in (("/sys/fs/cgroup/cpu.max", None), ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "/sys/fs/cgroup/cpu/cpu.cfs_period_us")):
+        try:
+            if period_path is None:
+                quota, period = open(quota_path).read().split()[:2]
+                if quota == "max":
+                    continue
+                quota, period = int(quota), int(period)
+            else:
+                quota, period = int(open(quota_path).read()), int(open(period_path).read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, -(-quota // period)))
+        except (OSError, ValueError):
+            pass
+    return max(1, min(n, 32))
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, nerr
+from conftest import GOLDEN, nerr, oracle_threads
 from oracle import restate, spec
 
 pytestmark = pytest.mark.gpu
@@ -90,7 +90,7 @@ def test_c1_512_frame_vs_oracle(dev, tensor_core):
     m, sd, opt = build(heads, "mot", dev, tensor_core=tensor_core)
     tol = TOL if tensor_core else TOL_ANCHOR
     x = spec.make_input((1, 3, 512, 512), tag="c1")
-    torch.set_num_threads(os.cpu_count() or 8)
+    torch.set_num_threads(oracle_threads())
     with torch.no_grad():
         ref_out, ref_fm = restate.dlaseg_forward(sd, x, heads)
     out, fm = m(x.to(dev))

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, nerr
+from conftest import GOLDEN, nerr, oracle_threads
 from oracle import restate, spec
 
 pytestmark = pytest.mark.gpu
@@ -54,7 +54,7 @@ def test_full_size_frame_vs_oracle_depth4(dev, name):
     from deft_b200.model.decode import generic_decode
     from deft_b200.pipeline import FramePipeline
     heads, dataset, (H, W), K, P, F, rows, T = FULL[name]
-    torch.set_num_threads(os.cpu_count() or 8)
+    torch.set_num_threads(oracle_threads())
     fallbacks0 = _lib.lib().deft_simt_fallback_count()
     m, sd, opt = build(heads, dataset, dev, max_object=P, K=K)
     kf, lsd = None, None
@@ -504,7 +504,7 @@ def test_dcn_halo_patch_kernel_vs_oracle(dev, chi, cho, h, w, n, off_scale):
     if off_scale > 1.0:
         sd["d.conv.conv_offset_mask.weight"] = sd["d.conv.conv_offset_mask.weight"] * off_scale
     x = spec.make_input((n, chi, h, w), tag=f"dcnpatch{chi}{cho}{h}")
-    torch.set_num_threads(os.cpu_count() or 8)
+    torch.set_num_threads(oracle_threads())
     with torch.no_grad():
         ref = restate.dcn_forward(sd, "d.conv", x, explicit=False)
     mod = DCN(chi, cho)
